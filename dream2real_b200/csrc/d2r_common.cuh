@@ -1,0 +1,88 @@
+// Shared host/device helpers for libd2r_b200 (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/d2r_b200.h"
+
+namespace d2r {
+
+// ---- error plumbing -----------------------------------------------------------------------------
+void set_error(const std::string& msg);
+extern thread_local unsigned long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
+
+#define D2R_CUDA(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ::d2r::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" +    \
+                             __FILE__ + ":" + std::to_string(__LINE__) + ")");                     \
+            return D2R_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+#define D2R_REQUIRE(cond, msg)                                                                     \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            ::d2r::set_error(std::string(msg));                                                    \
+            return D2R_ERR_INVALID;                                                                \
+        }                                                                                          \
+    } while (0)
+
+// ---- constants: reference include/neural-graphics-primitives/nerf_device.cuh:23-42 -------------
+constexpr uint32_t NERF_GRIDSIZE = 128;
+constexpr uint32_t NERF_GRID_N_CELLS = 128u * 128u * 128u;
+constexpr uint32_t NERF_CASCADES = 8;
+constexpr int MAX_LEVELS = 8;
+constexpr int N_FEAT = 4;
+
+struct Mat3x4 {     // NGP camera: columns 0..2 = rotation columns, column 3 = origin
+    float c[4][3];
+};
+
+struct ModelDev {
+    // hash grid
+    const __half* grid;                // [n_entries, 4]
+    uint32_t level_offset[MAX_LEVELS + 1];
+    float level_scale[MAX_LEVELS];
+    uint32_t level_res[MAX_LEVELS];
+    // MLP weights, fp16 row-major [out,in]
+    const __half* w_d0;  // [64,32]
+    const __half* w_d1;  // [16,64]
+    const __half* w_c0;  // [64,32]
+    const __half* w_c1;  // [64,64]
+    const __half* w_c2;  // [16,64]
+    const uint8_t* bitfield;           // [8 * 128^3 / 8]
+    float aabb_min[3], aabb_diag[3];
+    float raabb_min[3], raabb_max[3];
+    float r2l[9];
+    int r2l_identity;
+    int max_cascade;
+    float cone;
+    float min_transmittance;
+    float depth_scale;
+    float occ_min[3], occ_max[3];      // tight box of occupied cells
+};
+
+}  // namespace d2r
+
+struct d2r_model {
+    int device;
+    d2r::ModelDev dev;
+    void* params_dev;     // fp16 blob
+    uint8_t* bitfield_dev;
+    size_t n_params;
+    d2r_model_cfg cfg;
+};
+
+struct d2r_view {
+    int device;
+    int W, H;
+    float2* dirs_dev;     // [H*W] undistorted camera-plane (x, y), z == 1
+    d2r_camera cam;
+};

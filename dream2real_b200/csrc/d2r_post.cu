@@ -1,0 +1,246 @@
+// CLIP-side pre/post-processing kernels: rot90 + PIL-exact antialiased bicubic resize + normalise
+// (transformers CLIPImageProcessor, PIL backend, as called at reference clip_scoring.py:145-147,177)
+// and the logit / score arithmetic of clip_scoring.py:180-203.
+//
+// The resize restates Pillow's ImagingResample for 8-bit images (src/libImaging/Resample.c:
+// precompute_coeffs, normalize_coeffs_8bpc, ImagingResampleHorizontal_8bpc / Vertical_8bpc):
+// double-precision bicubic (a = -0.5) weights, normalised, quantised to 22 fractional bits,
+// integer accumulate with +0.5 rounding, clamp to u8 -- after the horizontal AND after the vertical
+// pass.  Integer arithmetic => bit-exact with PIL.  Pillow is a third-party dependency of the
+// reference (requirements.txt: Pillow==9.4.0), not vendored under /root/reference.
+#include <math.h>
+
+#include <vector>
+
+#include "d2r_common.cuh"
+
+namespace d2r {
+
+constexpr int PRECISION_BITS = 32 - 8 - 2;
+
+static double bicubic_filter(double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+}
+
+// Pillow precompute_coeffs + normalize_coeffs_8bpc for the full-image box
+static int precompute_coeffs(int inSize, int outSize, std::vector<int>& bounds, std::vector<int>& kk) {
+    const double in0 = 0.0, in1 = (double)inSize;
+    double scale = (in1 - in0) / outSize, filterscale = scale;
+    if (filterscale < 1.0) filterscale = 1.0;
+    const double support = 2.0 * filterscale;
+    const int ksize = (int)ceil(support) * 2 + 1;
+    bounds.assign((size_t)outSize * 2, 0);
+    kk.assign((size_t)outSize * ksize, 0);
+    std::vector<double> k(ksize);
+    for (int xx = 0; xx < outSize; ++xx) {
+        const double center = in0 + (xx + 0.5) * scale;
+        double ww = 0.0;
+        const double ss = 1.0 / filterscale;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > inSize) xmax = inSize;
+        xmax -= xmin;
+        int x;
+        for (x = 0; x < xmax; ++x) {
+            const double w = bicubic_filter((x + xmin - center + 0.5) * ss);
+            k[x] = w;
+            ww += w;
+        }
+        for (x = 0; x < xmax; ++x)
+            if (ww != 0.0) k[x] /= ww;
+        for (; x < ksize; ++x) k[x] = 0;
+        for (x = 0; x < ksize; ++x) {
+            const double v = k[x];
+            kk[(size_t)xx * ksize + x] = v < 0 ? (int)(-0.5 + v * (1 << PRECISION_BITS)) : (int)(0.5 + v * (1 << PRECISION_BITS));
+        }
+        bounds[xx * 2 + 0] = xmin;
+        bounds[xx * 2 + 1] = xmax;
+    }
+    return ksize;
+}
+
+__device__ __forceinline__ uint8_t clip8(int v) {
+    v >>= PRECISION_BITS;
+    return (uint8_t)min(max(v, 0), 255);
+}
+
+// horizontal pass over the (optionally rot90'd) image.  The rotated image is rot[i][j] = src[j][W-1-i]
+// (np.rot90 k=1 on the image axes); tmp layout is [K][R][Hr][3] with i fastest (coalesced both ways).
+__global__ void k_resize_h(const uint8_t* __restrict__ src, int H, int W, int rot90, int Hr, int Wr, int R, int ksize,
+                           const int* __restrict__ bounds, const int* __restrict__ kk, uint8_t* __restrict__ tmp) {
+    const int k = blockIdx.z;
+    const int xx = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Hr) return;
+    const uint8_t* img = src + (size_t)k * H * W * 3;
+    const int xmin = bounds[xx * 2], xmax = bounds[xx * 2 + 1];
+    const int* kr = kk + (size_t)xx * ksize;
+    int s0 = 1 << (PRECISION_BITS - 1), s1 = s0, s2 = s0;
+    for (int x = 0; x < xmax; ++x) {
+        const int j = xmin + x;
+        const uint8_t* p = rot90 ? img + ((size_t)j * W + (W - 1 - i)) * 3 : img + ((size_t)i * W + j) * 3;
+        const int w = kr[x];
+        s0 += p[0] * w; s1 += p[1] * w; s2 += p[2] * w;
+    }
+    uint8_t* o = tmp + (((size_t)k * R + xx) * Hr + i) * 3;
+    o[0] = clip8(s0); o[1] = clip8(s1); o[2] = clip8(s2);
+}
+
+// vertical pass + /255 + normalise, written patch-major fp16 (K padded to Kp columns) and optionally
+// as float32 pixel_values [K,3,R,R].
+__global__ void k_resize_v_norm(const uint8_t* __restrict__ tmp, int Hr, int R, int ksize, const int* __restrict__ bounds,
+                                const int* __restrict__ kk, int P, int Kp, float m0, float m1, float m2, float i0, float i1,
+                                float i2, __half* __restrict__ patches, float* __restrict__ pixels) {
+    const int k = blockIdx.z;
+    const int yy = blockIdx.y;
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xx >= R) return;
+    const int ymin = bounds[yy * 2], ymax = bounds[yy * 2 + 1];
+    const int* kr = kk + (size_t)yy * ksize;
+    const uint8_t* col = tmp + (((size_t)k * R + xx) * Hr + ymin) * 3;
+    int s0 = 1 << (PRECISION_BITS - 1), s1 = s0, s2 = s0;
+    for (int y = 0; y < ymax; ++y) {
+        const int w = kr[y];
+        s0 += col[y * 3 + 0] * w; s1 += col[y * 3 + 1] * w; s2 += col[y * 3 + 2] * w;
+    }
+    const uint8_t u[3] = {clip8(s0), clip8(s1), clip8(s2)};
+    const float mean[3] = {m0, m1, m2}, stdv[3] = {i0, i1, i2};
+    const int np_side = R / P;
+    const size_t prow = (size_t)k * np_side * np_side + (size_t)(yy / P) * np_side + xx / P;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        // transformers 4.27 image_transforms: rescale = (u8 * (1/255) in float64).astype(float32);
+        // normalize = (image - mean) / std in float32
+        const float v = (float)((double)u[c] * (1.0 / 255.0));
+        const float nv = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
+        if (patches) patches[prow * Kp + (size_t)c * P * P + (yy % P) * P + (xx % P)] = __float2half_rn(nv);
+        if (pixels) pixels[(((size_t)k * 3 + c) * R + yy) * R + xx] = nv;
+    }
+}
+
+__global__ void k_zero_pad_cols(__half* patches, size_t rows, int Kp, int K0) {
+    const size_t r = (size_t)blockIdx.x * blockDim.y + threadIdx.y;
+    if (r >= rows) return;
+    for (int c = K0 + threadIdx.x; c < Kp; c += blockDim.x) patches[r * Kp + c] = __float2half_rn(0.f);
+}
+
+// logits_per_image = exp(logit_scale) * img @ txt^T; score = mean(goal) / mean(norm)  (clip_scoring.py:180-203)
+__global__ void k_score(const float* __restrict__ img, const float* __restrict__ txt, int K, int Cn, int D, float scale, int n_goal,
+                        float* __restrict__ scores, float* __restrict__ logits) {
+    const int k = blockIdx.x;
+    extern __shared__ float s_logit[];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+    for (int c = warp; c < Cn; c += nw) {
+        float acc = 0.f;
+        for (int d = lane; d < D; d += 32) acc += img[(size_t)k * D + d] * txt[(size_t)c * D + d];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) { s_logit[c] = acc * scale; if (logits) logits[(size_t)k * Cn + c] = acc * scale; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float g = 0.f, n = 0.f;
+        for (int c = 0; c < n_goal; ++c) g += s_logit[c];
+        g /= (float)n_goal;
+        if (Cn > n_goal) {
+            for (int c = n_goal; c < Cn; ++c) n += s_logit[c];
+            n /= (float)(Cn - n_goal);
+            scores[k] = g / n;
+        } else {
+            scores[k] = g;
+        }
+    }
+}
+
+struct ResizePlan {
+    int in_size = 0, out_size = 0, ksize = 0;
+    int* bounds_dev = nullptr;
+    int* kk_dev = nullptr;
+};
+static ResizePlan g_plans[16][4];
+static uint8_t* g_tmp[16] = {nullptr};
+static size_t g_tmp_cap[16] = {0};
+
+static int get_plan(int device, int in_size, int out_size, ResizePlan** out) {
+    for (int i = 0; i < 4; ++i) {
+        ResizePlan& p = g_plans[device][i];
+        if (p.in_size == in_size && p.out_size == out_size && p.kk_dev) { *out = &p; return D2R_OK; }
+    }
+    for (int i = 0; i < 4; ++i) {
+        ResizePlan& p = g_plans[device][i];
+        if (p.kk_dev) continue;
+        std::vector<int> bounds, kk;
+        p.ksize = precompute_coeffs(in_size, out_size, bounds, kk);
+        p.in_size = in_size; p.out_size = out_size;
+        D2R_CUDA(cudaMalloc(&p.bounds_dev, bounds.size() * sizeof(int)));
+        D2R_CUDA(cudaMalloc(&p.kk_dev, kk.size() * sizeof(int)));
+        D2R_CUDA(cudaMemcpy(p.bounds_dev, bounds.data(), bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
+        D2R_CUDA(cudaMemcpy(p.kk_dev, kk.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice));
+        *out = &p;
+        return D2R_OK;
+    }
+    set_error("d2r_clip_preprocess: too many distinct resize plans");
+    return D2R_ERR_INVALID;
+}
+
+}  // namespace d2r
+
+using namespace d2r;
+
+extern "C" int d2r_clip_preprocess(const uint8_t* rgb_u8_dev, int K, int H, int W, int rot90, int R, int P, const float mean[3],
+                                   const float std_[3], void* patches_out_dev, float* pixels_f32_out_dev, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D2R_REQUIRE(rgb_u8_dev && mean && std_ && (patches_out_dev || pixels_f32_out_dev), "d2r_clip_preprocess: null argument");
+    D2R_REQUIRE(K > 0 && H > 0 && W > 0 && R > 0 && P > 0 && R % P == 0, "d2r_clip_preprocess: bad sizes");
+    D2R_REQUIRE(H == W, "d2r_clip_preprocess: only square renders are on this path (resize shortest edge == both edges)");
+    D2R_REQUIRE(K <= 65535, "d2r_clip_preprocess: K must be <= 65535 per call");
+    int device;
+    D2R_CUDA(cudaGetDevice(&device));
+    D2R_REQUIRE(device < 16, "d2r_clip_preprocess: device index too large");
+    const int Hr = rot90 ? W : H, Wr = rot90 ? H : W;
+    ResizePlan *ph, *pv;
+    int rc = get_plan(device, Wr, R, &ph);
+    if (rc) return rc;
+    rc = get_plan(device, Hr, R, &pv);
+    if (rc) return rc;
+    const size_t tmp_bytes = (size_t)K * R * Hr * 3;
+    if (tmp_bytes > g_tmp_cap[device]) {
+        if (g_tmp[device]) D2R_CUDA(cudaFree(g_tmp[device]));
+        D2R_CUDA(cudaMalloc(&g_tmp[device], tmp_bytes));
+        g_tmp_cap[device] = tmp_bytes;
+    }
+    {
+        dim3 grid((Hr + 127) / 128, R, K);
+        k_resize_h<<<grid, 128, 0, stream>>>(rgb_u8_dev, H, W, rot90, Hr, Wr, R, ph->ksize, ph->bounds_dev, ph->kk_dev, g_tmp[device]);
+    }
+    const int K0 = 3 * P * P, Kp = (K0 + 63) / 64 * 64;
+    {
+        dim3 grid((R + 127) / 128, R, K);
+        k_resize_v_norm<<<grid, 128, 0, stream>>>(g_tmp[device], Hr, R, pv->ksize, pv->bounds_dev, pv->kk_dev, P, Kp, mean[0], mean[1],
+                                                  mean[2], std_[0], std_[1], std_[2], (__half*)patches_out_dev, pixels_f32_out_dev);
+    }
+    count_launch(2);
+    if (patches_out_dev && Kp != K0) {
+        const size_t rows = (size_t)K * (R / P) * (R / P);
+        dim3 block(32, 8);
+        k_zero_pad_cols<<<(unsigned)((rows + 7) / 8), block, 0, stream>>>((__half*)patches_out_dev, rows, Kp, K0);
+        count_launch();
+    }
+    D2R_CUDA(cudaGetLastError());
+    return D2R_OK;
+}
+
+extern "C" int d2r_score(const float* img_embeds_dev, const float* txt_embeds_dev, int K, int C, int D, float logit_scale_exp, int n_goal,
+                         float* scores_out_dev, float* logits_out_dev, void* stream) {
+    D2R_REQUIRE(img_embeds_dev && txt_embeds_dev && scores_out_dev, "d2r_score: null argument");
+    D2R_REQUIRE(K > 0 && C > 0 && D > 0 && n_goal > 0 && n_goal <= C, "d2r_score: bad sizes");
+    k_score<<<K, 128, C * sizeof(float), (cudaStream_t)stream>>>(img_embeds_dev, txt_embeds_dev, K, C, D, logit_scale_exp, n_goal,
+                                                                scores_out_dev, logits_out_dev);
+    count_launch();
+    D2R_CUDA(cudaGetLastError());
+    return D2R_OK;
+}

@@ -1,0 +1,169 @@
+/*
+ * d2r_b200.h -- C ABI of libd2r_b200.so: the B200-native replacement for the native code on
+ * Dream2Real's imagination-and-scoring hot path.
+ *
+ * What it replaces (paths relative to /root/reference):
+ *   - the pybind11 module `pyngp` as far as the path uses it
+ *       reconstruction/instant-ngp/src/python_api.cu:123-201 (Testbed::render = render_to_cpu),
+ *       :382-566 (load_snapshot, set_nerf_camera_matrix, set_camera_to_training_view, ...);
+ *   - the NumPy/cv2 compositing in reconstruction/combined_rendering.py:117-155;
+ *   - the PIL/HF preprocessing + CLIPModel.forward + logit arithmetic in clip_scoring.py:145-203.
+ *
+ * Conventions:
+ *   - every function returns 0 on success, a negative d2r_status otherwise; the message is
+ *     available through d2r_last_error() (thread-local).  No C++ exception crosses the boundary.
+ *   - plain pointers and sizes only.  Pointers named *_dev are DEVICE pointers owned by the
+ *     caller (typically torch tensors); pointers named *_host are host pointers.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous w.r.t. the host unless
+ *     stated otherwise and never synchronise behind the caller's back (the *_host convenience
+ *     entry points do synchronise: they return host results).
+ *   - handles are not re-entrant; different handles / devices may be used concurrently.
+ */
+#ifndef D2R_B200_H
+#define D2R_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    D2R_OK = 0,
+    D2R_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+    D2R_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed      */
+    D2R_ERR_NOMEM = -3
+} d2r_status;
+
+typedef struct d2r_model d2r_model;   /* one Instant-NGP NeRF (hash grid + 2 MLPs + occupancy bitfield) */
+typedef struct d2r_view d2r_view;     /* one (training-view intrinsics, W x H) ray table                */
+typedef struct d2r_clip d2r_clip;     /* CLIP vision tower weights + workspaces                         */
+
+/* ---- model ---------------------------------------------------------------------------------- */
+/* Mirrors what Testbed::load_snapshot + reset_network leave on the device
+ * (reconstruction/instant-ngp/src/testbed.cu:4757-4871, :3613-3673; testbed_nerf.cu:2195-2231). */
+typedef struct {
+    int32_t n_levels;             /* 8   (configs/nerf/base.json:23-29)           */
+    int32_t n_features_per_level; /* 4                                             */
+    int32_t log2_hashmap_size;    /* 19                                            */
+    int32_t base_resolution;      /* 16                                            */
+    float per_level_scale;        /* exp(log(2048*aabb_scale/16)/7), testbed.cu:3668 */
+    int32_t max_cascade;          /* log2(aabb_scale), testbed_nerf.cu:2221-2224    */
+    float aabb_min[3], aabb_max[3];               /* m_aabb (training box, warp_position) */
+    float render_aabb_min[3], render_aabb_max[3]; /* m_render_aabb                        */
+    float render_aabb_to_local[9];                /* row-major 3x3                        */
+    float cone_angle_constant;    /* 1/256 if aabb_scale > 1 else 0, testbed_nerf.cu:2228 */
+    float min_transmittance;      /* nerf.render_min_transmittance, testbed.h:766 (0.01)  */
+    float depth_scale;            /* 1 / dataset.scale, testbed_nerf.cu:1888              */
+} d2r_model_cfg;
+
+/* params_f16_host: the snapshot's `params_binary` blob as-is: fp16
+ *   [density MLP 64x32,16x64 | rgb MLP 64x32,64x64,16x64 | hash grid]  (nerf_network.h:356-372).
+ * density_grid_f32_host: (max_cascade+1)*128^3 floats (snapshot `density_grid_binary` widened),
+ *   converted here to the occupancy bitfield exactly like testbed_nerf.cu:284-331,2355-2373.   */
+int d2r_model_load(const void* params_f16_host, size_t n_params,
+                   const float* density_grid_f32_host, size_t n_grid_cells,
+                   const d2r_model_cfg* cfg, int device, d2r_model** out);
+void d2r_model_free(d2r_model* m);
+/* nerf.render_min_transmittance may be changed after loading (combined_rendering.py:49). */
+int d2r_model_set_min_transmittance(d2r_model* m, float min_transmittance);
+/* Copy the 8-cascade occupancy bitfield (128^3/8*8 bytes) to the host -- parity tests. */
+int d2r_model_get_bitfield(const d2r_model* m, uint8_t* bitfield_host, size_t n_bytes);
+/* Tight box (in NGP coordinates) around every occupied cell of every cascade, clipped to the
+ * render aabb: rays that miss it can never take a sample. out6 = min xyz, max xyz.           */
+int d2r_model_get_occupied_aabb(const d2r_model* m, float* out6_host);
+
+/* ---- view ----------------------------------------------------------------------------------- */
+/* State after set_camera_to_training_view(v) for a W x H render (testbed.cu:453-468,4065-4072):
+ * focal = metadata.focal_length / resolution[fov_axis] * {W,H}[fov_axis] * zoom; screen_center =
+ * principal point fraction; lens = the view's OpenCV (k1,k2,p1,p2) or perspective.
+ * Builds the per-pixel camera-plane direction table (Newton lens undistortion,
+ * common_device.cuh:289-333,393-431) once; every candidate pose then only rotates it.         */
+typedef struct {
+    int32_t width, height;
+    float focal[2];
+    float screen_center[2];
+    int32_t lens_mode;       /* 0 = perspective, 1 = OpenCV */
+    float lens_params[4];
+} d2r_camera;
+int d2r_view_prepare(const d2r_camera* cam, int device, d2r_view** out);
+void d2r_view_free(d2r_view* v);
+int d2r_view_get_dirs(const d2r_view* v, float* dirs_xy_host /* [H*W*2] */);
+
+/* ---- render --------------------------------------------------------------------------------- */
+#define D2R_MODE_SHADE 1
+#define D2R_MODE_DEPTH 2
+/* K renders of one model from K cameras = K x Testbed::render(W,H,1,linear=True) per mode
+ * (python_api.cu:123-201).  cams_ngp_host: [K,3,4] float, ALREADY in NGP convention
+ * (nerf_matrix_to_ngp applied, nerf_loader.h:101-121).  background_rgba: Testbed.background_color.
+ * rgba_out_dev / depth_out_dev: [K,H,W,4] float32 linear premultiplied (NULL = skip that mode);
+ * both modes come out of ONE march.  n_samples_out_dev (optional, uint64 device): sample counter. */
+int d2r_render(const d2r_model* m, const d2r_view* v, const float* cams_ngp_host, int K,
+               const float background_rgba[4], float* rgba_out_dev, float* depth_out_dev,
+               unsigned long long* n_samples_out_dev, void* stream);
+
+/* Fused candidate render + depth-test composite + colour post-process =
+ * reconstruction/combined_rendering.py:117-155 for K candidate poses of the movable object:
+ *   fg Shade + fg Depth (one march), fg_d<0.05 -> 100, bg_d<0.05 -> 100, fg where fg_d < bg_d,
+ *   rgb/a, linear_to_srgb (scripts/common.py:142-144), u8 = clip*255+0.5, alpha_u8 < 130 -> 0.
+ * bg_rgba_dev [H,W,4] / bg_depth_dev [H,W]: the cached background render and depth map.
+ * rgb_u8_out_dev: [K,H,W,3] uint8.                                                             */
+int d2r_render_composite(const d2r_model* fg, const d2r_view* v, const float* cams_ngp_host, int K,
+                         const float fg_background_rgba[4], const float* bg_rgba_dev,
+                         const float* bg_depth_dev, uint8_t* rgb_u8_out_dev,
+                         unsigned long long* n_samples_out_dev, void* stream);
+
+/* ---- CLIP preprocessing ----------------------------------------------------------------------
+ * np.rot90(k=1, axes=(1,2)) (clip_scoring.py:145) then transformers CLIPImageProcessor (PIL
+ * backend): resize shortest side -> R with PIL BICUBIC (antialiased, u8 fixed-point two-pass),
+ * centre crop R, /255, (x-mean)/std.  Output is written patch-major for the ViT patch-embed GEMM:
+ * patches_out_dev [K * (R/P)^2, 3*P*P] fp16, row = k*(R/P)^2 + py*(R/P)+px, col = c*P*P+iy*P+ix.
+ * pixels_f32_out_dev (optional): [K,3,R,R] float32 "pixel_values" for parity checks.            */
+int d2r_clip_preprocess(const uint8_t* rgb_u8_dev, int K, int H, int W, int rot90, int R, int P,
+                        const float mean[3], const float std[3], void* patches_out_dev,
+                        float* pixels_f32_out_dev, void* stream);
+
+/* ---- CLIP vision tower ----------------------------------------------------------------------- */
+typedef struct {
+    int32_t image_size;    /* 224 | 336 */
+    int32_t patch_size;    /* 32  | 14  */
+    int32_t hidden;        /* 768 | 1024 */
+    int32_t heads;         /* 12  | 16  */
+    int32_t layers;        /* 12  | 24  */
+    int32_t mlp;           /* 3072 | 4096 */
+    int32_t proj;          /* 512 | 768 */
+    float ln_eps;          /* 1e-5 */
+    int32_t max_batch;     /* images per forward call (workspace sizing) */
+} d2r_clip_cfg;
+
+/* Weight order (all float32 host pointers, HF transformers CLIPVisionModelWithProjection names):
+ *  0 embeddings.patch_embedding.weight [hidden,3,P,P]   1 embeddings.class_embedding [hidden]
+ *  2 embeddings.position_embedding.weight [T,hidden]    3,4 pre_layrnorm.{weight,bias}
+ *  then per layer l (16 tensors): ln1.{w,b}, q.{w,b}, k.{w,b}, v.{w,b}, out_proj.{w,b},
+ *                                 ln2.{w,b}, fc1.{w,b}, fc2.{w,b}
+ *  then post_layernorm.{weight,bias}, visual_projection.weight [proj,hidden].                  */
+int d2r_clip_load(const d2r_clip_cfg* cfg, const float* const* weights_host, int n_weights,
+                  int device, d2r_clip** out);
+void d2r_clip_free(d2r_clip* c);
+/* patches_dev: output of d2r_clip_preprocess for K <= max_batch images.
+ * embeds_out_dev: [K, proj] float32, L2-normalised image embeddings (CLIPModel.forward).       */
+int d2r_clip_encode(d2r_clip* c, const void* patches_dev, int K, float* embeds_out_dev, void* stream);
+
+/* logits_per_image = exp(logit_scale) * img . txt^T; score = mean(goal logits)/mean(norm logits)
+ * (clip_scoring.py:180-203).  n_goal = number of leading goal captions (1, or #templates);
+ * C == n_goal -> score is the mean goal logit.  logits_out_dev optional [K,C].                 */
+int d2r_score(const float* img_embeds_dev, const float* txt_embeds_dev, int K, int C, int D,
+              float logit_scale_exp, int n_goal, float* scores_out_dev, float* logits_out_dev,
+              void* stream);
+
+/* ---- misc ------------------------------------------------------------------------------------ */
+const char* d2r_last_error(void);
+/* number of kernels this library has launched on the calling thread since the last reset */
+unsigned long long d2r_launch_count(int reset);
+const char* d2r_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D2R_B200_H */
