@@ -1,0 +1,244 @@
+// fp16 x fp16 -> fp32 GEMM on the 5th-generation tensor cores: C[M,N] = A[M,K] . B[N,K]^T (+ epilogue).
+// Both operands K-major ("TN"), i.e. activations [rows, features] times nn.Linear weights [out, in].
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads, 2 CTAs per SM so one CTA's epilogue
+// overlaps the other's main loop):
+//   warp 0      TMA producer : cp.async.bulk.tensor 2-D loads (128B swizzle) into a 3-stage smem ring,
+//                              completion via mbarrier complete_tx
+//   warp 1      MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//                              (M=128, N=BN, K=16) x4 per 64-wide k block; accumulator in TMEM;
+//                              tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 2..5  epilogue     : tcgen05.ld (32 lanes x 32 columns) -> bias / quick-GELU / residual ->
+//                              global stores
+// Used for every dense contraction of the CLIP vision tower (reference clip_scoring.py:180-181 ->
+// transformers CLIPModel.forward -> nn.Linear / patch-embedding conv).
+#include <dlfcn.h>
+
+#include <mutex>
+
+#include "d2r_common.cuh"
+#include "d2r_gemm.cuh"
+#include "d2r_gemm_api.h"
+
+namespace d2r {
+
+constexpr int BM = 128, BK = 64, STAGES = 3, GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmSmem {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 128 + 1024;   // barriers + tmem slot + alignment slack
+};
+
+struct GemmArgs {
+    int M, N, K;
+    const float* bias;     // [N] or null
+    __half* out_f16;       // modes 0,1
+    float* out_f32;        // modes 2 (in-place residual), 3
+    int ldo;               // leading dimension of the output (elements)
+    int mode;
+};
+
+__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }   // x * sigmoid(1.702 x)
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+k_gemm_f16(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
+    using S = GemmSmem<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B needs 1024-byte aligned tiles
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int num_kb = g.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+                unsigned char* sa = smem + s * S::STAGE_BYTES;
+                mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
+                tma_load_2d(sa, &tma_a, &full_bar[s], kb * BK, m0);
+                tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(BM, BN, /*fp16*/ 0);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+                const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(a_addr + S::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)   // advance 16 elements = 32 bytes = 2 descriptor units along K
+                    umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                tc_commit(&empty_bar[s]);           // smem stage free once these MMAs retire
+            }
+            tc_commit(tmem_full_bar);               // accumulator complete
+        }
+    } else {
+        // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+            if (row < g.M) {
+                const int col0 = n0 + c * 32;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (g.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(g.bias + col0 + j);
+                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                    }
+                }
+                if (g.mode == GEMM_OUT_F16 || g.mode == GEMM_OUT_F16_QUICKGELU) {
+                    if (g.mode == GEMM_OUT_F16_QUICKGELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+                    }
+                    __half* o = g.out_f16 + (size_t)row * g.ldo + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 pk;
+                        __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                        __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(o + j) = pk;
+                    }
+                } else {
+                    float* o = g.out_f32 + (size_t)row * g.ldo + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (g.mode == GEMM_RESIDUAL_F32) {
+                            const float4 old = *reinterpret_cast<const float4*>(o + j);
+                            t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+                        }
+                        *reinterpret_cast<float4*>(o + j) = t;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static int get_encode() {
+    std::call_once(g_encode_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            g_encode = (PFN_encodeTiled)fn;
+    });
+    if (!g_encode) { set_error("cuTensorMapEncodeTiled is not available from the CUDA driver"); return D2R_ERR_CUDA; }
+    return D2R_OK;
+}
+
+// 2-D fp16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle, OOB -> zeros
+int make_tmap_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+    int rc = get_encode();
+    if (rc) return rc;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld_elems * sizeof(__half)};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " (base must be 16-byte aligned, "
+                  "row pitch a multiple of 16 bytes)");
+        return D2R_ERR_CUDA;
+    }
+    return D2R_OK;
+}
+
+template <int BN>
+static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t stream) {
+    static bool attr_done[16] = {false};
+    int dev;
+    D2R_CUDA(cudaGetDevice(&dev));
+    if (!attr_done[dev & 15]) {
+        D2R_CUDA(cudaFuncSetAttribute(k_gemm_f16<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
+        attr_done[dev & 15] = true;
+    }
+    dim3 grid((g.M + BM - 1) / BM, g.N / BN);
+    k_gemm_f16<BN><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(ta, tb, g);
+    count_launch();
+    D2R_CUDA(cudaGetLastError());
+    return D2R_OK;
+}
+
+int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const float* bias, int mode, void* out, int ldo,
+             cudaStream_t stream) {
+    D2R_REQUIRE(A && B && out, "gemm_f16: null argument");
+    D2R_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_f16: empty problem");
+    D2R_REQUIRE(K % BK == 0, "gemm_f16: K must be a multiple of 64 (pad the operands)");
+    D2R_REQUIRE(N % 64 == 0, "gemm_f16: N must be a multiple of 64");
+    D2R_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0, "gemm_f16: leading dimensions must be multiples of 8 elements");
+    D2R_REQUIRE(mode >= 0 && mode <= 3, "gemm_f16: bad epilogue mode");
+    const int BN = (N % 128 == 0) ? 128 : 64;
+    CUtensorMap ta, tb;
+    int rc = make_tmap_f16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);
+    if (rc) return rc;
+    rc = make_tmap_f16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)BN);
+    if (rc) return rc;
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K; g.bias = bias; g.mode = mode; g.ldo = ldo;
+    g.out_f16 = (mode == GEMM_OUT_F16 || mode == GEMM_OUT_F16_QUICKGELU) ? (__half*)out : nullptr;
+    g.out_f32 = (mode == GEMM_RESIDUAL_F32 || mode == GEMM_OUT_F32) ? (float*)out : nullptr;
+    return BN == 128 ? launch_gemm_bn<128>(ta, tb, g, stream) : launch_gemm_bn<64>(ta, tb, g, stream);
+}
+
+}  // namespace d2r
+
+extern "C" int d2r_gemm_f16(const void* a_dev, int lda, const void* b_dev, int ldb, int M, int N, int K, const float* bias_dev, int mode,
+                            void* out_dev, int ldo, void* stream) {
+    return d2r::gemm_f16((const __half*)a_dev, lda, (const __half*)b_dev, ldb, M, N, K, bias_dev, mode, out_dev, ldo, (cudaStream_t)stream);
+}

@@ -157,6 +157,13 @@ int d2r_score(const float* img_embeds_dev, const float* txt_embeds_dev, int K, i
               float logit_scale_exp, int n_goal, float* scores_out_dev, float* logits_out_dev,
               void* stream);
 
+/* ---- building block exported for tests: the tcgen05 GEMM every ViT contraction runs on ----------
+ * out = A[M,K] . B[N,K]^T (+bias[N]); A, B fp16 K-major device pointers with leading dimensions
+ * lda/ldb (elements); K % 64 == 0, N % 64 == 0.  mode: 0 fp16 out, 1 fp16 quick-GELU out,
+ * 2 fp32 in-place residual add, 3 fp32 out.                                                     */
+int d2r_gemm_f16(const void* a_dev, int lda, const void* b_dev, int ldb, int M, int N, int K,
+                 const float* bias_dev, int mode, void* out_dev, int ldo, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char* d2r_last_error(void);
 /* number of kernels this library has launched on the calling thread since the last reset */
