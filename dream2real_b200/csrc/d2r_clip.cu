@@ -282,10 +282,10 @@ template <int NJ>
 static int launch_attention(const d2r_clip* c, int B, cudaStream_t stream) {
     const int T = c->T, d = c->cfg.hidden;
     const size_t smem = (size_t)T * 66 * 2 + (size_t)T * 64 * 2;
-    static bool done[16] = {false};
-    if (!done[c->device & 15]) {
+    static size_t granted[16] = {0};   // the attribute is a limit: only ever raise it
+    if (smem > granted[c->device & 15]) {
         D2R_CUDA(cudaFuncSetAttribute(k_attention<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        done[c->device & 15] = true;
+        granted[c->device & 15] = smem;
     }
     dim3 grid(B, c->cfg.heads);
     k_attention<NJ><<<grid, 128, smem, stream>>>(c->qkv, T, d, c->o);

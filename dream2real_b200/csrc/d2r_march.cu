@@ -38,6 +38,7 @@ struct MarchParams {
     const float* bg_depth;         //                 cached background depth  [H,W]
     uint8_t* u8_out;               //                 [K,H,W,3]
     unsigned long long* n_samples;
+    unsigned long long* prof;      // profiling counters {samples, tiles} or null
 };
 
 // shared-memory plan (floats): fp32 copies of the fp16 MLP weights, row-major [out][in]
@@ -279,9 +280,13 @@ __global__ void __launch_bounds__(CTA, 3) k_march(const __grid_constant__ MarchP
         if (P.depth_out) P.depth_out[o] = depth;
         if (P.u8_out) composite_pixel(shade, depth.x, __ldg(P.bg_rgba + idx), __ldg(P.bg_depth + idx), P.u8_out + o * 3);
     }
-    if (P.n_samples) {
+    if (P.n_samples || P.prof) {
         for (int o = 16; o > 0; o >>= 1) my_samples += __shfl_xor_sync(0xffffffffu, my_samples, o);
-        if ((tid & 31) == 0 && my_samples) atomicAdd(P.n_samples, my_samples);
+        if ((tid & 31) == 0 && my_samples) {
+            if (P.n_samples) atomicAdd(P.n_samples, my_samples);
+            if (P.prof) atomicAdd(P.prof, my_samples);
+        }
+        if (P.prof && blockIdx.x == 0 && tid == 0) atomicAdd(P.prof + 1, (unsigned long long)total_tiles);
     }
 }
 
@@ -393,6 +398,15 @@ __global__ void k_view_ranges(int W, int H, const float2* __restrict__ dirs, flo
     }
 }
 
+// ---- profiling: CUDA events around the march kernel only (bench.py roofline) ----------------------
+struct Prof {
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    size_t used = 0;
+    unsigned long long* counters = nullptr;   // device {samples, tiles}
+};
+static Prof g_prof[16];
+
 // ---- host launcher -------------------------------------------------------------------------------
 struct Scratch {   // per-device scratch reused across calls (grown on demand)
     Mat3x4* cams = nullptr; int4* bbox = nullptr; uint32_t* tiles = nullptr; uint32_t* prefix = nullptr;
@@ -487,13 +501,59 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
         D2R_CUDA(cudaFuncSetAttribute(k_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_set[m->device] = true;
     }
+    Prof& pf = g_prof[m->device];
+    P.prof = pf.on ? pf.counters : nullptr;
+    std::pair<cudaEvent_t, cudaEvent_t>* evp = nullptr;
+    if (pf.on) {
+        if (pf.used == pf.ev.size()) {
+            cudaEvent_t a, b;
+            D2R_CUDA(cudaEventCreate(&a));
+            D2R_CUDA(cudaEventCreate(&b));
+            pf.ev.emplace_back(a, b);
+        }
+        evp = &pf.ev[pf.used++];
+        D2R_CUDA(cudaEventRecord(evp->first, stream));
+    }
     k_march<<<s.n_sm * 3, CTA, SMEM_BYTES, stream>>>(P);
+    if (evp) D2R_CUDA(cudaEventRecord(evp->second, stream));
     count_launch();
     D2R_CUDA(cudaGetLastError());
     return D2R_OK;
 }
 
 }  // namespace d2r
+
+extern "C" int d2r_profile_enable(int device, int on) {
+    D2R_REQUIRE(device >= 0 && device < 16, "d2r_profile_enable: bad device");
+    d2r::Prof& pf = d2r::g_prof[device];
+    D2R_CUDA(cudaSetDevice(device));
+    if (on && !pf.counters) D2R_CUDA(cudaMalloc(&pf.counters, 2 * sizeof(unsigned long long)));
+    if (pf.counters) D2R_CUDA(cudaMemset(pf.counters, 0, 2 * sizeof(unsigned long long)));
+    pf.used = 0;
+    pf.on = on != 0;
+    return D2R_OK;
+}
+
+extern "C" int d2r_profile_read(int device, float* march_ms_total, int* n_launches, unsigned long long* n_samples,
+                                unsigned long long* n_tiles) {
+    D2R_REQUIRE(device >= 0 && device < 16 && march_ms_total && n_launches && n_samples && n_tiles, "d2r_profile_read: bad argument");
+    d2r::Prof& pf = d2r::g_prof[device];
+    D2R_CUDA(cudaSetDevice(device));
+    float total = 0.f;
+    for (size_t i = 0; i < pf.used; ++i) {
+        D2R_CUDA(cudaEventSynchronize(pf.ev[i].second));
+        float ms = 0.f;
+        D2R_CUDA(cudaEventElapsedTime(&ms, pf.ev[i].first, pf.ev[i].second));
+        total += ms;
+    }
+    unsigned long long c[2] = {0, 0};
+    if (pf.counters) D2R_CUDA(cudaMemcpy(c, pf.counters, sizeof(c), cudaMemcpyDeviceToHost));
+    *march_ms_total = total;
+    *n_launches = (int)pf.used;
+    *n_samples = c[0];
+    *n_tiles = c[1];
+    return D2R_OK;
+}
 
 extern "C" int d2r_render(const d2r_model* m, const d2r_view* v, const float* cams_ngp_host, int K, const float background_rgba[4],
                           float* rgba_out_dev, float* depth_out_dev, unsigned long long* n_samples_out_dev, void* stream) {

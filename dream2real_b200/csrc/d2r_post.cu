@@ -161,30 +161,24 @@ struct ResizePlan {
     int* bounds_dev = nullptr;
     int* kk_dev = nullptr;
 };
-static ResizePlan g_plans[16][4];
+static std::vector<ResizePlan> g_plans[16];
 static uint8_t* g_tmp[16] = {nullptr};
 static size_t g_tmp_cap[16] = {0};
 
-static int get_plan(int device, int in_size, int out_size, ResizePlan** out) {
-    for (int i = 0; i < 4; ++i) {
-        ResizePlan& p = g_plans[device][i];
-        if (p.in_size == in_size && p.out_size == out_size && p.kk_dev) { *out = &p; return D2R_OK; }
-    }
-    for (int i = 0; i < 4; ++i) {
-        ResizePlan& p = g_plans[device][i];
-        if (p.kk_dev) continue;
-        std::vector<int> bounds, kk;
-        p.ksize = precompute_coeffs(in_size, out_size, bounds, kk);
-        p.in_size = in_size; p.out_size = out_size;
-        D2R_CUDA(cudaMalloc(&p.bounds_dev, bounds.size() * sizeof(int)));
-        D2R_CUDA(cudaMalloc(&p.kk_dev, kk.size() * sizeof(int)));
-        D2R_CUDA(cudaMemcpy(p.bounds_dev, bounds.data(), bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
-        D2R_CUDA(cudaMemcpy(p.kk_dev, kk.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice));
-        *out = &p;
-        return D2R_OK;
-    }
-    set_error("d2r_clip_preprocess: too many distinct resize plans");
-    return D2R_ERR_INVALID;
+static int get_plan(int device, int in_size, int out_size, ResizePlan* out) {
+    for (const ResizePlan& p : g_plans[device])
+        if (p.in_size == in_size && p.out_size == out_size) { *out = p; return D2R_OK; }
+    ResizePlan p;
+    std::vector<int> bounds, kk;
+    p.ksize = precompute_coeffs(in_size, out_size, bounds, kk);
+    p.in_size = in_size; p.out_size = out_size;
+    D2R_CUDA(cudaMalloc(&p.bounds_dev, bounds.size() * sizeof(int)));
+    D2R_CUDA(cudaMalloc(&p.kk_dev, kk.size() * sizeof(int)));
+    D2R_CUDA(cudaMemcpy(p.bounds_dev, bounds.data(), bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
+    D2R_CUDA(cudaMemcpy(p.kk_dev, kk.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice));
+    g_plans[device].push_back(p);
+    *out = p;
+    return D2R_OK;
 }
 
 }  // namespace d2r
@@ -202,11 +196,12 @@ extern "C" int d2r_clip_preprocess(const uint8_t* rgb_u8_dev, int K, int H, int 
     D2R_CUDA(cudaGetDevice(&device));
     D2R_REQUIRE(device < 16, "d2r_clip_preprocess: device index too large");
     const int Hr = rot90 ? W : H, Wr = rot90 ? H : W;
-    ResizePlan *ph, *pv;
-    int rc = get_plan(device, Wr, R, &ph);
+    ResizePlan ph_, pv_;
+    int rc = get_plan(device, Wr, R, &ph_);
     if (rc) return rc;
-    rc = get_plan(device, Hr, R, &pv);
+    rc = get_plan(device, Hr, R, &pv_);
     if (rc) return rc;
+    const ResizePlan *ph = &ph_, *pv = &pv_;
     const size_t tmp_bytes = (size_t)K * R * Hr * 3;
     if (tmp_bytes > g_tmp_cap[device]) {
         if (g_tmp[device]) D2R_CUDA(cudaFree(g_tmp[device]));

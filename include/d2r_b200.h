@@ -164,6 +164,12 @@ int d2r_score(const float* img_embeds_dev, const float* txt_embeds_dev, int K, i
 int d2r_gemm_f16(const void* a_dev, int lda, const void* b_dev, int ldb, int M, int N, int K,
                  const float* bias_dev, int mode, void* out_dev, int ldo, void* stream);
 
+/* ---- measurement hooks (bench.py roofline): CUDA events around the march kernel alone, recorded on
+ * the launching stream, plus device counters of network samples and 16x8 ray tiles processed.   */
+int d2r_profile_enable(int device, int on);   /* also resets the accumulated state */
+int d2r_profile_read(int device, float* march_ms_total, int* n_launches,
+                     unsigned long long* n_samples, unsigned long long* n_tiles);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char* d2r_last_error(void);
 /* number of kernels this library has launched on the calling thread since the last reset */

@@ -577,10 +577,26 @@ class RenderStats:
     n_hit: int = 0
 
 
+def occupied_box(bitfield: np.ndarray, max_cascade: int, pad: float = 1e-3):
+    """Tight NGP-space box around every occupied cell of cascades 0..max_cascade (the cull the CUDA path
+    uses: a ray that misses it can never take a sample, so skipping it cannot change any pixel)."""
+    lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+    n = NERF_GRID_N_CELLS
+    for c in range(max_cascade + 1):
+        cells = np.nonzero(np.unpackbits(bitfield[c * (n // 8):(c + 1) * (n // 8)], bitorder="little"))[0].astype(u32)
+        if cells.size == 0:
+            continue
+        xyz = np.stack([morton3D_invert(cells), morton3D_invert(cells >> u32(1)), morton3D_invert(cells >> u32(2))], 1).astype(np.float64)
+        size = 2.0 ** c
+        lo = np.minimum(lo, 0.5 - size / 2 + size * xyz.min(0) / 128.0)
+        hi = np.maximum(hi, 0.5 - size / 2 + size * (xyz.max(0) + 1) / 128.0)
+    return (lo - pad).astype(f32), (hi + pad).astype(f32)
+
+
 def render(snap, bitfield: np.ndarray, vs: ViewSetup, cam_nerf_34, mode: str = SHADE,
            background_color=None, min_transmittance: float = 0.01, accum: str = "fp16_k16",
            plane_dirs: Optional[np.ndarray] = None, pixel_mask: Optional[np.ndarray] = None,
-           stats: Optional[RenderStats] = None, both: bool = False):
+           stats: Optional[RenderStats] = None, both: bool = False, cull_box=None):
     """Returns float32 [H, W, 4] linear premultiplied RGBA, exactly what pyngp hands Python.
 
     both=True returns (shade, depth) from one march (identical sample sets -- the reference
@@ -605,6 +621,14 @@ def render(snap, bitfield: np.ndarray, vs: ViewSetup, cam_nerf_34, mode: str = S
     p0 = (o + t[:, None] * d).astype(f32)
     lp0 = p0 if ident else (p0 @ r2l.T).astype(f32)
     alive = np.all((lp0 >= ra_min) & (lp0 <= ra_max), axis=-1)
+    if cull_box is not None:      # optional, result-preserving: see occupied_box()
+        FMAX = np.finfo(f32).max
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            t0_ = ((cull_box[0] - o) / d).astype(f32)
+            t1_ = ((cull_box[1] - o) / d).astype(f32)
+        tn = np.max(np.minimum(t0_, t1_), axis=-1)
+        tf = np.min(np.maximum(t0_, t1_), axis=-1)
+        alive &= (tn <= tf) & (tf >= 0) & (tn < FMAX)
     cone = f32(snap.cone_angle_constant)
     with np.errstate(divide="ignore"):
         idir = (f32(1.0) / d).astype(f32)

@@ -1,0 +1,113 @@
+"""-m gpu: the whole hot path through the reference-facing call surface (renderer(...).render,
+optimise_pose_grid / score_poses) against the full CPU oracle pipeline on the same seeded scene."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _tiny_clip(seed=5):
+    import torch
+    from transformers import CLIPConfig, CLIPModel, CLIPTextConfig, CLIPVisionConfig
+    v = CLIPVisionConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, image_size=64,
+                         patch_size=32, projection_dim=64)
+    t = CLIPTextConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2, projection_dim=64, vocab_size=1000)
+    c = CLIPConfig(text_config=t.to_dict(), vision_config=v.to_dict(), projection_dim=64)
+    c._attn_implementation = "eager"
+    torch.manual_seed(seed)
+    m = CLIPModel(c).eval()
+    with torch.no_grad():
+        m.logit_scale.fill_(2.0)
+        # random image/text embeddings are near-orthogonal, which makes goal/norm an ill-conditioned ratio; a shared
+        # bias direction keeps every logit well away from zero like trained CLIP similarities (~0.2-0.3)
+        m.visual_projection.weight.mul_(0.2)
+    return m
+
+
+def test_optimise_pose_grid_matches_oracle_pipeline(tmp_path):
+    import torch
+    from dream2real_b200 import clip_scoring, ingp, synth
+    from dream2real_b200.reconstruction.combined_rendering import renderer
+    from oracle import ngp_oracle as O
+    from oracle import post_oracle as PO
+    d = str(tmp_path)
+    res = 72
+    scene = synth.make_scene("shopping", d, log2_hashmap_size=14, seed=21)
+    tm = synth.SyntheticTaskModel(scene, "goal caption", ["normalising caption"], torch.device("cuda"))
+    model = _tiny_clip()
+    ids = torch.randint(3, 900, (2, 7))
+    ids[:, -1] = 2
+    sample_res = [4, 3, 1, 1, 1, 1]
+    r = renderer(d, tm, resolution=res)
+    best_pose, pose_batch, pose_scores = clip_scoring.optimise_pose_grid(
+        r, tm.depths[:1], [0], tm, d, sample_res=sample_res, phys_check=synth.all_valid_phys_check, scene_type=3,
+        smoothing=True, clip_model=model, text_inputs={"input_ids": ids}, save_renders=True)
+    assert best_pose.shape == (4, 4) and pose_batch.shape == (12, 16) and pose_scores.shape == (12,)
+    # cache-compatible artefacts (combined_rendering.py:157-159, clip_scoring.py:222-223)
+    assert sorted(os.listdir(os.path.join(d, "cb_render"))) == [f"cb_rgb_{i:04d}.png" for i in range(12)]
+    assert os.path.exists(os.path.join(d, "best_render.png"))
+
+    # ---- oracle pipeline on the CPU -------------------------------------------------------------------
+    model = model.cpu()
+    fg, bg = ingp.load_snapshot(os.path.join(d, "fg_base.ingp")), ingp.load_snapshot(os.path.join(d, "bg_base.ingp"))
+    vs = O.view_setup(bg, 0, res, res)
+    dirs = O.camera_plane_dirs(vs)
+    fgb, _ = O.build_bitfield(fg.density_grid, fg.max_cascade)
+    bgb, _ = O.build_bitfield(bg.density_grid, bg.max_cascade)
+    poses = PO.sample_poses_grid(scene["scene_centre"], sample_res, 3)
+    assert torch.equal(poses, pose_batch.cpu())
+    vp = PO.converter(poses.numpy().reshape(-1, 4, 4).astype(np.float64))
+    rp = PO.converter(scene["opt_cam_poses"][:1])
+    bg_img = O.render(bg, bgb, vs, rp[0][:3], mode=O.SHADE, background_color=[0, 0, 0, 1], plane_dirs=dirs)
+    bg_d = PO.background_depth(scene["depths"][0], scene["movable_masks"][0], (res, res))
+    T1 = PO.converter(scene["fg_pose"][None])[0]
+    imgs = []
+    for i in range(12):
+        cam = PO.convert_virtual_pose(T1, vp[i], rp[0])
+        sh = O.render(fg, fgb, vs, cam[:3], mode=O.SHADE, background_color=[0, 0, 0, 0], plane_dirs=dirs)
+        dp = O.render(fg, fgb, vs, cam[:3], mode=O.DEPTH, background_color=[0, 0, 0, 0], plane_dirs=dirs)
+        imgs.append(PO.composite(bg_img, bg_d, sh, dp[..., 0]))
+    imgs = np.stack(imgs)
+    # the PNGs the product wrote are its renders: compare pixel-wise with the oracle's
+    import cv2
+    got = np.stack([cv2.cvtColor(cv2.imread(os.path.join(d, "cb_render", f"cb_rgb_{i:04d}.png")), cv2.COLOR_BGR2RGB) for i in range(12)])
+    diff = np.abs(got.astype(int) - imgs.astype(int))
+    print("u8 render diff: >1 LSB on", float((diff > 1).mean()), "max", diff.max())
+    assert (diff > 1).mean() < 5e-3
+    px = PO.clip_preprocess(np.rot90(imgs, k=1, axes=(1, 2)), 64)
+    logits = PO.clip_logits(model, px, ids)
+    ref_scores = PO.normalise_scores(logits, 1)
+    ref_smooth = PO.spatially_smooth_heatmap(ref_scores.clone(), sample_res)
+    rel = ((pose_scores - ref_smooth).abs() / ref_smooth.abs().clamp(min=1e-6)).max().item()
+    print("score rel err", rel)
+    assert rel < 2e-3
+    assert int(torch.argmax(pose_scores)) == int(torch.argmax(ref_smooth))
+    assert torch.equal(best_pose.cpu(), poses[int(torch.argmax(ref_smooth))].view(4, 4))
+
+
+def test_use_cache_renders_and_aliases(tmp_path):
+    import torch
+    from dream2real_b200 import clip_scoring, synth
+    from dream2real_b200.reconstruction import ngp_visual_model
+    from dream2real_b200.reconstruction.combined_rendering import renderer
+    assert clip_scoring.score_poses is clip_scoring.optimise_pose_grid
+    assert ngp_visual_model.get_visual_model is ngp_visual_model.get_vis_ngps
+    d = str(tmp_path)
+    scene = synth.make_scene("pool_triangle", d, log2_hashmap_size=12, seed=2)
+    tm = synth.SyntheticTaskModel(scene, "goal", None, torch.device("cuda"))
+    model = _tiny_clip(9)
+    ids = torch.randint(3, 900, (1, 5))
+    ids[:, -1] = 2
+    kw = dict(sample_res=[3, 2, 1, 1, 1, 1], phys_check=synth.all_valid_phys_check, scene_type=0, smoothing=False, clip_model=model,
+              text_inputs={"input_ids": ids})
+    r = renderer(d, tm, resolution=64)
+    _, _, s1 = clip_scoring.optimise_pose_grid(r, None, [0], tm, d, **kw)            # depths_gt=None -> NeRF depth for the bg
+    np.savetxt(os.path.join(d, "pose_scores.txt"), s1.numpy())
+    _, _, s2 = clip_scoring.optimise_pose_grid(r, None, [0], tm, d, use_cache_renders=True, **kw)
+    assert torch.allclose(s1, s2, rtol=1e-5, atol=1e-6)                              # PNG round trip is lossless
+    with pytest.raises(Exception):
+        clip_scoring.optimise_pose_grid(r, None, [0], tm, d, **dict(kw, phys_check=lambda p, t, v: torch.zeros_like(v)))
+    best, _, ones = clip_scoring.optimise_pose_grid(r, None, [0], tm, d, physics_only=True, **kw)
+    assert best.shape == (4, 4) and torch.all(ones == 1)

@@ -1,0 +1,158 @@
+"""-m gpu parity tests of everything after the ray march: depth-test composite, rot90 + PIL-exact
+preprocessing, the tcgen05 ViT forward, the score kernel -- each through the C ABI, each against the
+oracle (numpy / real Pillow / HuggingFace CLIPModel fp32 eager) on the same seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _tiny_clip(seed=0):
+    import torch
+    from transformers import CLIPConfig, CLIPModel, CLIPTextConfig, CLIPVisionConfig
+    v = CLIPVisionConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, image_size=64,
+                         patch_size=32, projection_dim=64)
+    t = CLIPTextConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2, projection_dim=64, vocab_size=1000)
+    c = CLIPConfig(text_config=t.to_dict(), vision_config=v.to_dict(), projection_dim=64)
+    c._attn_implementation = "eager"
+    torch.manual_seed(seed)
+    m = CLIPModel(c).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if k.endswith("bias") or "norm" in k:
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+    return m
+
+
+@pytest.mark.parametrize("H,R,P", [(800, 224, 32), (400, 336, 14), (336, 336, 14), (96, 64, 32)])
+def test_preprocess_bit_exact_vs_pillow(H, R, P):
+    import torch
+    from dream2real_b200 import _native as N
+    from dream2real_b200.clip import OPENAI_CLIP_MEAN, OPENAI_CLIP_STD
+    from oracle import post_oracle as PO
+    rng = np.random.default_rng(H + R)
+    K = 3
+    imgs = rng.integers(0, 256, size=(K, H, H, 3), dtype=np.uint8)
+    imgs[1, : H // 2] = 0            # the alpha<130 -> black regions of real renders
+    d = torch.from_numpy(imgs).cuda()
+    kp = (3 * P * P + 63) // 64 * 64
+    npatch = (R // P) ** 2
+    patches = torch.full((K * npatch, kp), 7.0, dtype=torch.float16, device="cuda")
+    pix = torch.empty((K, 3, R, R), dtype=torch.float32, device="cuda")
+    N.check(N.lib().d2r_clip_preprocess(d.data_ptr(), K, H, H, 1, R, P, N.f4(OPENAI_CLIP_MEAN), N.f4(OPENAI_CLIP_STD),
+                                        patches.data_ptr(), pix.data_ptr(), N.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = PO.clip_preprocess(np.rot90(imgs, k=1, axes=(1, 2)), R)           # clip_scoring.py:145 then the processor
+    got = pix.cpu().numpy()
+    # u8 resampling is integer arithmetic -> identical u8 -> identical float up to the last-bit of (x-mean)/std
+    assert np.abs(got - ref).max() < 1e-6, np.abs(got - ref).max()
+    # patch-major fp16 copy: conv-as-GEMM layout [k*np + py*side + px, c*P*P + iy*P + ix], zero padded
+    side = R // P
+    pm = got.reshape(K, 3, side, P, side, P).transpose(0, 2, 4, 1, 3, 5).reshape(K * npatch, 3 * P * P)
+    pg = patches.cpu().float().numpy()
+    assert np.abs(pg[:, : 3 * P * P] - pm.astype(np.float16).astype(np.float32)).max() == 0
+    assert np.all(pg[:, 3 * P * P:] == 0)
+
+
+def test_score_kernel_vs_oracle():
+    import torch
+    from dream2real_b200.clip import ClipVision
+    from oracle import post_oracle as PO
+    m = _tiny_clip()
+    cv = ClipVision(m, max_batch=8)
+    torch.manual_seed(0)
+    common = torch.randn(64, device="cuda")          # keeps the normalising logits away from 0 (the ratio is ill-conditioned there)
+    img = torch.nn.functional.normalize(torch.randn(37, 64, device="cuda") + 2 * common, dim=-1)
+    txt = torch.nn.functional.normalize(torch.randn(4, 64, device="cuda") + 2 * common, dim=-1)
+    for n_goal in (1, 2, 4):
+        s, logits = cv.score(img, txt, n_goal=n_goal, want_logits=True)
+        ref_logits = m.logit_scale.exp().item() * img @ txt.t()
+        assert (logits - ref_logits).abs().max().item() < 1e-4
+        ref = PO.normalise_scores(ref_logits.cpu(), n_goal)
+        assert ((s.cpu() - ref).abs() / ref.abs().clamp(min=1)).max().item() < 1e-5
+
+
+def _clip_parity(model, K, seed, tol_cos, tol_logit_rel):
+    import torch
+    from dream2real_b200.clip import ClipVision, text_embeds
+    from oracle import post_oracle as PO
+    R = model.config.vision_config.image_size
+    rng = np.random.default_rng(seed)
+    H = 2 * R - 16
+    imgs = rng.integers(0, 256, size=(K, H, H, 3), dtype=np.uint8)
+    ids = torch.randint(3, 900, (3, 9))
+    ids[:, -1] = 2                       # eos (config default eos_token_id == 2 -> legacy argmax pooling)
+    # oracle: rot90 -> PIL processor -> HF CLIPModel fp32 on CPU
+    px = PO.clip_preprocess(np.rot90(imgs, k=1, axes=(1, 2)), R)
+    ref_logits = PO.clip_logits(model, px, ids)
+    with torch.no_grad():
+        vo = model.vision_model(pixel_values=torch.from_numpy(px))
+        ref_emb = model.visual_projection(vo.pooler_output)
+        ref_emb = ref_emb / ref_emb.norm(dim=-1, keepdim=True)
+    # product
+    cv = ClipVision(model, max_batch=max(4, K // 2))      # forces two batches
+    emb = cv.encode_images(torch.from_numpy(imgs).cuda(), rot90=True)
+    cos_err = (1 - (emb.cpu() * ref_emb).sum(-1)).abs().max().item()
+    txt = text_embeds(model, ids)
+    _, logits = cv.score(emb, txt.cuda(), n_goal=1, want_logits=True)
+    cos_img_txt = (emb.cpu() @ txt.t() - ref_emb @ txt.t()).abs().max().item()
+    scale = float(ref_logits.abs().max())
+    logit_err = (logits.cpu() - ref_logits).abs().max().item()
+    print(f"clip parity: 1-cos(emb) {cos_err:.2e}  |cos(img,txt) err| {cos_img_txt:.2e}  logit err {logit_err:.2e} of {scale:.1f}")
+    assert cos_img_txt < tol_cos          # north-star: 1e-4 cosine-score error
+    assert logit_err < tol_logit_rel * max(scale, 1.0)
+    return cos_img_txt
+
+
+def test_clip_tiny_vs_hf():
+    _clip_parity(_tiny_clip(3), K=6, seed=1, tol_cos=1e-4, tol_logit_rel=2e-3)
+
+
+def test_clip_vit_b32_vs_hf():
+    from dream2real_b200.clip import make_hf_clip
+    _clip_parity(make_hf_clip("ViT-B/32", seed=7, vocab_size=1000), K=4, seed=2, tol_cos=1e-4, tol_logit_rel=2e-3)
+
+
+@pytest.fixture(scope="module")
+def scene(tmp_path_factory):
+    from dream2real_b200 import synth
+    d = str(tmp_path_factory.mktemp("shop"))
+    return synth.make_scene("shopping", d, log2_hashmap_size=14, seed=5)
+
+
+def test_composite_kernel_vs_numpy_oracle(scene):
+    """d2r_render_composite == oracle composite of d2r_render's float outputs (combined_rendering.py:133-155)."""
+    import torch
+    from dream2real_b200 import synth
+    from dream2real_b200.reconstruction.combined_rendering import convert_virtual_pose, renderer
+    from dream2real_b200.utils import accio2ngp
+    from oracle import post_oracle as PO
+    tm = synth.SyntheticTaskModel(scene, "goal", ["norm"], torch.device("cuda"))
+    r = renderer(scene["dir"], tm, resolution=120)
+    poses = np.stack([scene["fg_pose"].copy() for _ in range(5)])
+    poses[:, :3, 3] = [[0.5, 0.0, 0.04], [0.36, -0.16, 0.04], [0.62, 0.08, 0.04], [0.45, 0.05, 0.12], [0.9, 0.5, 0.04]]
+    vp = accio2ngp.converter(poses)
+    rp = accio2ngp.converter(scene["opt_cam_poses"][:1])
+    out = r.render(vp, rp, [0], tm.depths[:1], tm.movable_masks, save=False)
+    assert len(out) == 5 and out[0].shape == (120, 120, 3) and out[0].dtype == np.uint8
+    # oracle composite from the float renders of the same kernels
+    bg_img, bg_d = r.render_background(rp[0], 0, tm.depths[0], tm.movable_masks[0])
+    fg = tm.movable_obj.vis_model
+    fg.set_camera_to_training_view(0)
+    T1 = accio2ngp.converter(scene["fg_pose"][None])[0]
+    n_diff = 0
+    for i in range(5):
+        cam = convert_virtual_pose(T1, vp[i], rp[0])
+        sh, dp = fg.render_batch(cam[None, :3, :], 120, 120)
+        ref = PO.composite(bg_img.cpu().numpy(), bg_d.cpu().numpy(), sh[0].cpu().numpy(), dp[0, :, :, 0].cpu().numpy())
+        n_diff += int((np.abs(ref.astype(int) - out[i].astype(int)) > 0).sum())
+        assert np.abs(ref.astype(int) - out[i].astype(int)).max() <= 1
+    assert n_diff <= 5 * 120 * 120 * 3 * 1e-3
+    # the object is visible in candidate 0 and differs from the pure background image
+    assert (out[0].astype(int) - out[4].astype(int)).any()
+    # background depth: reference cv2 path
+    ref_d = PO.background_depth(scene["depths"][0], scene["movable_masks"][0], (120, 120))
+    assert np.array_equal(ref_d, bg_d.cpu().numpy())
