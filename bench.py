@@ -223,7 +223,7 @@ def run_ours(args):
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     # algorithmic bytes of the march kernel: 512 B of hash-table reads per network
     # sample + 23 B per primary ray it owns (20 B cached background rgba+depth read, 3 B u8 written)
-    rays = int(nt.value) * 128
+    rays = int(nt.value)          # primary rays (pixels of the candidates' screen rectangles) the kernel owned
     alg_bytes = int(ns.value) * 512 + rays * 23
     march_s = mm.value / 1e3
     achieved = alg_bytes / march_s / 1e9 if march_s > 0 else 0.0

@@ -1,9 +1,9 @@
 // fp16 x fp16 -> fp32 GEMM on the 5th-generation tensor cores: C[M,N] = A[M,K] . B[N,K]^T (+ epilogue).
 // Both operands K-major ("TN"), i.e. activations [rows, features] times nn.Linear weights [out, in].
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads, 2 CTAs per SM so one CTA's epilogue
-// overlaps the other's main loop):
-//   warp 0      TMA producer : cp.async.bulk.tensor 2-D loads (128B swizzle) into a 3-stage smem ring,
+// Structure (persistent: one CTA per SM walks 128 x BN output tiles; 192 threads; two TMEM accumulators
+// so the epilogue of one tile overlaps the main loop of the next):
+//   warp 0      TMA producer : cp.async.bulk.tensor 2-D loads (128B swizzle) into a 6-stage smem ring,
 //                              completion via mbarrier complete_tx
 //   warp 1      MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16
 //                              (M=128, N=BN, K=16) x4 per 64-wide k block; accumulator in TMEM;
@@ -14,6 +14,7 @@
 // transformers CLIPModel.forward -> nn.Linear / patch-embedding conv).
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "d2r_common.cuh"
@@ -22,15 +23,16 @@
 
 namespace d2r {
 
-constexpr int BM = 128, BK = 64, STAGES = 3, GEMM_THREADS = 192;
+constexpr int BM = 128, BK = 64, GEMM_THREADS = 192;
 
 template <int BN>
 struct GemmSmem {
+    static constexpr int STAGES = BN == 128 ? 6 : 8;          // 6 x 32 KB / 8 x 24 KB
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + 128 + 1024;   // barriers + tmem slot + alignment slack
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + tmem slot + alignment slack
 };
 
 struct GemmArgs {
@@ -44,30 +46,36 @@ struct GemmArgs {
 
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }   // x * sigmoid(1.702 x)
 
+// Persistent: grid = #SMs, every CTA walks output tiles (n fastest, so CTAs running together share the
+// same rows of A through L2); TMEM holds TWO accumulators so the epilogue of tile i overlaps the main
+// loop of tile i+1.
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_f16(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
     using S = GemmSmem<BN>;
+    constexpr int STAGES = S::STAGES;
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B needs 1024-byte aligned tiles
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int num_kb = g.K / BK;
+    const int tiles_n = g.N / BN, tiles_m = (g.M + BM - 1) / BM;
+    const int num_tiles = tiles_n * tiles_m;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -75,89 +83,109 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CU
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
-                unsigned char* sa = smem + s * S::STAGE_BYTES;
-                mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
-                tma_load_2d(sa, &tma_a, &full_bar[s], kb * BK, m0);
-                tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kb * BK, n0);
+            uint32_t it = 0;   // running k-block counter across tiles -> stage / phase
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES;
+                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                    unsigned char* sa = smem + s * S::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
+                    tma_load_2d(sa, &tma_a, &full_bar[s], kb * BK, m0);
+                    tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(BM, BN, /*fp16*/ 0);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+            uint32_t it = 0, tile_it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+                const uint32_t acc = tile_it & 1;
+                mbar_wait(&tmem_empty_bar[acc], ((tile_it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-                const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(a_addr + S::A_BYTES);
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+                    const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(a_addr + S::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)   // advance 16 elements = 32 bytes = 2 descriptor units along K
-                    umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                tc_commit(&empty_bar[s]);           // smem stage free once these MMAs retire
+                    for (int k = 0; k < BK / 16; ++k)   // advance 16 elements = 32 bytes = 2 descriptor units along K
+                        umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    tc_commit(&empty_bar[s]);           // smem stage free once these MMAs retire
+                }
+                tc_commit(&tmem_full_bar[acc]);         // accumulator complete
             }
-            tc_commit(tmem_full_bar);               // accumulator complete
         }
     } else {
         // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
+        uint32_t tile_it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            const uint32_t acc = tile_it & 1;
+            const int row = m0 + q * 32 + lane;
+            mbar_wait(&tmem_full_bar[acc], (tile_it >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-            tmem_ld_wait();
-            if (row < g.M) {
-                const int col0 = n0 + c * 32;
-                float v[32];
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
+                tmem_ld_wait();
+                if (row < g.M) {
+                    const int col0 = n0 + c * 32;
+                    float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (g.bias) {
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (g.bias) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = *reinterpret_cast<const float4*>(g.bias + col0 + j);
-                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                    }
-                }
-                if (g.mode == GEMM_OUT_F16 || g.mode == GEMM_OUT_F16_QUICKGELU) {
-                    if (g.mode == GEMM_OUT_F16_QUICKGELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-                    }
-                    __half* o = g.out_f16 + (size_t)row * g.ldo + col0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 pk;
-                        __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-                        __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(o + j) = pk;
-                    }
-                } else {
-                    float* o = g.out_f32 + (size_t)row * g.ldo + col0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        if (g.mode == GEMM_RESIDUAL_F32) {
-                            const float4 old = *reinterpret_cast<const float4*>(o + j);
-                            t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(g.bias + col0 + j);
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
                         }
-                        *reinterpret_cast<float4*>(o + j) = t;
+                    }
+                    if (g.mode == GEMM_OUT_F16 || g.mode == GEMM_OUT_F16_QUICKGELU) {
+                        if (g.mode == GEMM_OUT_F16_QUICKGELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+                        }
+                        __half* o = g.out_f16 + (size_t)row * g.ldo + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                            __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(o + j) = pk;
+                        }
+                    } else {
+                        float* o = g.out_f32 + (size_t)row * g.ldo + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            if (g.mode == GEMM_RESIDUAL_F32) {
+                                const float4 old = *reinterpret_cast<const float4*>(o + j);
+                                t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+                            }
+                            *reinterpret_cast<float4*>(o + j) = t;
+                        }
                     }
                 }
             }
+            // this warp is done reading the accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<BN>(tmem_base);
+        tmem_dealloc<2 * BN>(tmem_base);
     }
 }
 
@@ -208,8 +236,10 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
         D2R_CUDA(cudaFuncSetAttribute(k_gemm_f16<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
         attr_done[dev & 15] = true;
     }
-    dim3 grid((g.M + BM - 1) / BM, g.N / BN);
-    k_gemm_f16<BN><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(ta, tb, g);
+    static int n_sm[16] = {0};
+    if (!n_sm[dev & 15]) D2R_CUDA(cudaDeviceGetAttribute(&n_sm[dev & 15], cudaDevAttrMultiProcessorCount, dev));
+    const int num_tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
+    k_gemm_f16<BN><<<std::min(num_tiles, n_sm[dev & 15]), GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(ta, tb, g);
     count_launch();
     D2R_CUDA(cudaGetLastError());
     return D2R_OK;

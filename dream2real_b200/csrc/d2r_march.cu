@@ -15,6 +15,10 @@
 #include <algorithm>
 #include <vector>
 
+#include <stdlib.h>
+#include <string.h>
+
+#include "d2r_gemm.cuh"
 #include "d2r_march.cuh"
 
 namespace d2r {
@@ -38,7 +42,7 @@ struct MarchParams {
     const float* bg_depth;         //                 cached background depth  [H,W]
     uint8_t* u8_out;               //                 [K,H,W,3]
     unsigned long long* n_samples;
-    unsigned long long* prof;      // profiling counters {samples, tiles} or null
+    unsigned long long* prof;      // profiling counters {samples, primary rays owned, work items} or null
 };
 
 // shared-memory plan (floats): fp32 copies of the fp16 MLP weights, row-major [out][in]
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(CTA, 3) k_march(const __grid_constant__ MarchP
             r.ix = 1.0f / r.dx; r.iy = 1.0f / r.dy; r.iz = 1.0f / r.dz;
         }
         bool alive;
-        float t;
+        float t, t_box = 0.f;
         {
             float lox = r.ox, loy = r.oy, loz = r.oz, ldx = r.dx, ldy = r.dy, ldz = r.dz;
             if (!M.r2l_identity) {
@@ -175,12 +179,15 @@ __global__ void __launch_bounds__(CTA, 3) k_march(const __grid_constant__ MarchP
             if (alive) {
                 const float2 oc = box_ray_intersect(M.occ_min, M.occ_max, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
                 if (oc.x > 1e37f || oc.y < 0.f) alive = false;
+                t_box = oc.x;
+                r.t_exit = oc.y;
             }
         }
         const float cone = M.cone;   // calc_cone_angle returns the constant (nerf_device.cuh:369-376)
         // ---- advance_pos_nerf (testbed_nerf.cu:333-362) ----
         if (alive) {
             t = advance_n_steps(t, cone, ld_random_val0(idx * 786433u));
+            t = fast_forward_to_box(t, cone, t_box);
             t = skip_to_occupied(t, cone, r, M);
             if (t >= MAX_DEPTH()) alive = false;
         }
@@ -286,9 +293,13 @@ __global__ void __launch_bounds__(CTA, 3) k_march(const __grid_constant__ MarchP
             if (P.n_samples) atomicAdd(P.n_samples, my_samples);
             if (P.prof) atomicAdd(P.prof, my_samples);
         }
-        if (P.prof && blockIdx.x == 0 && tid == 0) atomicAdd(P.prof + 1, (unsigned long long)total_tiles);
+        if (P.prof && blockIdx.x == 0 && tid == 0) atomicAdd(P.prof + 1, (unsigned long long)total_tiles * CTA);
     }
 }
+
+}  // namespace d2r
+#include "d2r_march_tc.cuh"
+namespace d2r {
 
 // ---- per-candidate screen rectangle + tile prefix ---------------------------------------------------
 // Conservative: contains every pixel whose (undistorted) camera-plane direction lies inside the
@@ -298,11 +309,11 @@ __global__ void k_candidate_bbox(int K, int W, int H, const Mat3x4* __restrict__
                                  const float* __restrict__ col_hi, const float* __restrict__ row_lo,
                                  const float* __restrict__ row_hi, const float occ_min_x, const float occ_min_y,
                                  const float occ_min_z, const float occ_max_x, const float occ_max_y, const float occ_max_z,
-                                 int full_frame, int4* __restrict__ bbox, uint32_t* __restrict__ tiles) {
+                                 int seg_mode, int4* __restrict__ bbox, uint32_t* __restrict__ tiles) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
     int x0 = 0, y0 = 0, x1 = W - 1, y1 = H - 1;
-    if (!full_frame) {
+    {
         const Mat3x4 C = cams[k];
         float u0 = 1e30f, u1 = -1e30f, v0 = 1e30f, v1 = -1e30f;
         bool behind = false;
@@ -330,7 +341,15 @@ __global__ void k_candidate_bbox(int K, int W, int H, const Mat3x4* __restrict__
         }
     }
     uint32_t n = 0;
-    if (x1 >= x0 && y1 >= y0) n = (uint32_t)((x1 - x0 + TILE_W) / TILE_W) * (uint32_t)((y1 - y0 + TILE_H) / TILE_H);
+    if (x1 >= x0 && y1 >= y0) {
+        if (seg_mode) {   // k_march_tc work items: bands of rows holding ~TC_SEG_PIXELS pixels
+            const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+            const int seg_rows = max(1, (TC_SEG_PIXELS + bw - 1) / bw);
+            n = (uint32_t)((bh + seg_rows - 1) / seg_rows);
+        } else {
+            n = (uint32_t)((x1 - x0 + TILE_W) / TILE_W) * (uint32_t)((y1 - y0 + TILE_H) / TILE_H);
+        }
+    }
     else { x0 = 0; y0 = 0; x1 = -1; y1 = -1; }
     bbox[k] = make_int4(x0, y0, x1, y1);
     tiles[k] = n;
@@ -358,22 +377,24 @@ __global__ void k_tile_prefix(int K, const uint32_t* __restrict__ tiles, uint32_
     if (tid == 0) *counter = 0;
 }
 
-// pixels outside a candidate's rectangle: constant background blend (render) / background composite (u8)
-__global__ void k_fill_outside(int K, int W, int H, const int4* __restrict__ bbox, float4 shade_bg, float4 depth_bg,
-                               float4* __restrict__ rgba_out, float4* __restrict__ depth_out,
-                               const uint8_t* __restrict__ bg_u8, uint8_t* __restrict__ u8_out) {
+// Every frame starts as a copy of the composited background (u8) / the constant background blend (float);
+// the march kernel then overwrites the pixels of the candidate's rectangle.  Pure streaming stores:
+// 128-bit vectors whenever a frame is a whole number of 16-byte words.
+__global__ void k_fill_frames(int K, int W, int H, float4 shade_bg, float4 depth_bg, float4* __restrict__ rgba_out,
+                              float4* __restrict__ depth_out, const uint8_t* __restrict__ bg_u8, uint8_t* __restrict__ u8_out, int vec_ok) {
     const int k = blockIdx.x;
-    const int4 bb = bbox[k];
-    const size_t base = (size_t)k * W * H;
-    for (int p = blockIdx.y * blockDim.x + threadIdx.x; p < W * H; p += gridDim.y * blockDim.x) {
-        const int x = p % W, y = p / W;
-        if (x >= bb.x && x <= bb.z && y >= bb.y && y <= bb.w) continue;
-        if (rgba_out) rgba_out[base + p] = shade_bg;
-        if (depth_out) depth_out[base + p] = depth_bg;
-        if (u8_out) {
-            u8_out[(base + p) * 3 + 0] = bg_u8[p * 3 + 0];
-            u8_out[(base + p) * 3 + 1] = bg_u8[p * 3 + 1];
-            u8_out[(base + p) * 3 + 2] = bg_u8[p * 3 + 2];
+    const size_t npx = (size_t)W * H;
+    const size_t stride = (size_t)gridDim.y * blockDim.x, first = (size_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (rgba_out) for (size_t p = first; p < npx; p += stride) rgba_out[(size_t)k * npx + p] = shade_bg;
+    if (depth_out) for (size_t p = first; p < npx; p += stride) depth_out[(size_t)k * npx + p] = depth_bg;
+    if (u8_out) {
+        const size_t bytes = npx * 3;
+        if (vec_ok) {
+            const uint4* __restrict__ src = reinterpret_cast<const uint4*>(bg_u8);
+            uint4* __restrict__ dst = reinterpret_cast<uint4*>(u8_out + (size_t)k * bytes);
+            for (size_t i = first; i < bytes / 16; i += stride) dst[i] = __ldg(src + i);
+        } else {
+            for (size_t i = first; i < bytes; i += stride) u8_out[(size_t)k * bytes + i] = bg_u8[i];
         }
     }
 }
@@ -403,7 +424,7 @@ struct Prof {
     bool on = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
     size_t used = 0;
-    unsigned long long* counters = nullptr;   // device {samples, tiles}
+    unsigned long long* counters = nullptr;   // device {samples, rays, items}
 };
 static Prof g_prof[16];
 
@@ -472,8 +493,10 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
         s.ranges_view = (const void*)v->dirs_dev;
     }
     const ModelDev& M = m->dev;
+    // D2R_MARCH=simt selects the round-1 CUDA-core kernel (kept for A/B measurements); default: tensor-core kernel
+    static const bool use_tc = []() { const char* e = getenv("D2R_MARCH"); return !(e && strcmp(e, "simt") == 0); }();
     k_candidate_bbox<<<(K + 127) / 128, 128, 0, stream>>>(K, W, H, s.cams, col_lo, col_hi, row_lo, row_hi, M.occ_min[0], M.occ_min[1],
-                                                          M.occ_min[2], M.occ_max[0], M.occ_max[1], M.occ_max[2], 0, s.bbox, s.tiles);
+                                                          M.occ_min[2], M.occ_max[0], M.occ_max[1], M.occ_max[2], use_tc ? 1 : 0, s.bbox, s.tiles);
     k_tile_prefix<<<1, 1024, 0, stream>>>(K, s.tiles, s.prefix, s.counter);
     count_launch(2);
 
@@ -486,8 +509,9 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
         count_launch();
     }
     {
-        dim3 grid(K, std::min((W * H + 255) / 256, 64));
-        k_fill_outside<<<grid, 256, 0, stream>>>(K, W, H, s.bbox, empty, empty, (float4*)rgba_out, (float4*)depth_out, s.bg_u8, u8_out);
+        dim3 grid(K, std::min((W * H * 3 / 16 + 255) / 256 + 1, 32));
+        const int vec_ok = ((size_t)W * H * 3) % 16 == 0 && ((uintptr_t)u8_out % 16) == 0 && ((uintptr_t)s.bg_u8 % 16) == 0;
+        k_fill_frames<<<grid, 256, 0, stream>>>(K, W, H, empty, empty, (float4*)rgba_out, (float4*)depth_out, s.bg_u8, u8_out, vec_ok);
         count_launch();
     }
     MarchParams P;
@@ -499,6 +523,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     static bool attr_set[16] = {false};
     if (!attr_set[m->device]) {
         D2R_CUDA(cudaFuncSetAttribute(k_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        D2R_CUDA(cudaFuncSetAttribute(k_march_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_TOTAL));
         attr_set[m->device] = true;
     }
     Prof& pf = g_prof[m->device];
@@ -514,7 +539,8 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
         evp = &pf.ev[pf.used++];
         D2R_CUDA(cudaEventRecord(evp->first, stream));
     }
-    k_march<<<s.n_sm * 3, CTA, SMEM_BYTES, stream>>>(P);
+    if (use_tc) k_march_tc<<<s.n_sm * 4, TC_THREADS, TS_TOTAL, stream>>>(P);
+    else k_march<<<s.n_sm * 3, CTA, SMEM_BYTES, stream>>>(P);
     if (evp) D2R_CUDA(cudaEventRecord(evp->second, stream));
     count_launch();
     D2R_CUDA(cudaGetLastError());
@@ -527,8 +553,8 @@ extern "C" int d2r_profile_enable(int device, int on) {
     D2R_REQUIRE(device >= 0 && device < 16, "d2r_profile_enable: bad device");
     d2r::Prof& pf = d2r::g_prof[device];
     D2R_CUDA(cudaSetDevice(device));
-    if (on && !pf.counters) D2R_CUDA(cudaMalloc(&pf.counters, 2 * sizeof(unsigned long long)));
-    if (pf.counters) D2R_CUDA(cudaMemset(pf.counters, 0, 2 * sizeof(unsigned long long)));
+    if (on && !pf.counters) D2R_CUDA(cudaMalloc(&pf.counters, 4 * sizeof(unsigned long long)));
+    if (pf.counters) D2R_CUDA(cudaMemset(pf.counters, 0, 4 * sizeof(unsigned long long)));
     pf.used = 0;
     pf.on = on != 0;
     return D2R_OK;
