@@ -85,71 +85,128 @@ __global__ void k_layernorm_f16(const float* __restrict__ x, const float* __rest
     warp_layernorm_row<__half>(x + (size_t)row * in_row_stride, d, w, b, eps, out + (size_t)row * d, threadIdx.x % 32);
 }
 
-// softmax(q k^T) v for one (image, head); q already carries the 1/sqrt(head_dim) scale.
-// K/V of the head live in shared memory (fp16), scores / probabilities in fp32 registers.
-template <int NJ>   // ceil(T / 32)
+// softmax(q k^T) v, flash-attention style, for head_dim 64; q already carries the 1/sqrt(head_dim)
+// scale.  One CTA = 64 query rows of one (image, head); each of the 4 warps owns 16 rows and walks the
+// keys in blocks of 64: S = Q.K^T and O += P.V on the warp-level tensor-core path (mma.sync m16n8k16,
+// fp16 operands, fp32 accumulate), online softmax in fp32 registers.  The ViT contractions proper (98 %
+// of the FLOPs at T = 50) run on tcgen05 (d2r_gemm.cu); a 50 x 50 x 64 problem per head does not fill
+// an M = 128 UMMA tile, which is why the attention core uses warp MMAs.
+constexpr int ATT_HD = 64, ATT_BQ = 64, ATT_BK = 64, ATT_LD = 72;   // smem row pitch (halves): 144 B, conflict-free ldmatrix
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const __half* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const __half* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 __global__ void __launch_bounds__(128) k_attention(const __half* __restrict__ qkv, int T, int d, __half* __restrict__ out) {
-    constexpr int HD = 64, KS = 66;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __half* Ks = reinterpret_cast<__half*>(smem_raw);
-    __half* Vs = Ks + (size_t)T * KS;
-    const int img = blockIdx.x, head = blockIdx.y;
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const __half* base = qkv + (size_t)img * T * 3 * d + head * HD;
-    for (int i = threadIdx.x; i < T * (HD / 2); i += blockDim.x) {
-        const int t = i / (HD / 2), c2 = i % (HD / 2);
-        const __half2 kv = *reinterpret_cast<const __half2*>(base + (size_t)t * 3 * d + d + c2 * 2);
-        const __half2 vv = *reinterpret_cast<const __half2*>(base + (size_t)t * 3 * d + 2 * d + c2 * 2);
-        *reinterpret_cast<__half2*>(Ks + (size_t)t * KS + c2 * 2) = kv;
-        *reinterpret_cast<__half2*>(Vs + (size_t)t * HD + c2 * 2) = vv;
+    __shared__ __align__(16) __half Qs[ATT_BQ * ATT_LD];
+    __shared__ __align__(16) __half Ks[ATT_BK * ATT_LD];
+    __shared__ __align__(16) __half Vs[ATT_BK * ATT_LD];
+    const int img = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * ATT_BQ;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const __half* base = qkv + (size_t)img * T * 3 * d + head * ATT_HD;
+    // stage this CTA's query rows (zero beyond T)
+    for (int i = tid; i < ATT_BQ * (ATT_HD / 8); i += 128) {
+        const int r = i / (ATT_HD / 8), c8 = i % (ATT_HD / 8);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (q0 + r < T) v = *reinterpret_cast<const uint4*>(base + (size_t)(q0 + r) * 3 * d + c8 * 8);
+        *reinterpret_cast<uint4*>(Qs + r * ATT_LD + c8 * 8) = v;
     }
     __syncthreads();
-    for (int r = warp; r < T; r += 4) {
-        float2 q[HD / 2];
-        const __half2* qp = reinterpret_cast<const __half2*>(base + (size_t)r * 3 * d);
+    uint32_t qf[4][4];   // A fragments of this warp's 16 rows, 4 k-steps of 16 dims
 #pragma unroll
-        for (int c = 0; c < HD / 2; ++c) q[c] = __half22float2(qp[c]);
-        float s[NJ];
-        float mx = -INFINITY;
+    for (int kk = 0; kk < 4; ++kk) ldmatrix_x4(qf[kk], Qs + (warp * 16 + (lane & 15)) * ATT_LD + kk * 16 + (lane >> 4) * 8);
+    float o[8][4];
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) {
-            const int j = jj * 32 + lane;
-            float acc = -INFINITY;
-            if (j < T) {
-                acc = 0.f;
-                const __half2* kp = reinterpret_cast<const __half2*>(Ks + (size_t)j * KS);
-#pragma unroll
-                for (int c = 0; c < HD / 2; ++c) {
-                    const float2 kk = __half22float2(kp[c]);
-                    acc = fmaf(q[c].x, kk.x, acc);
-                    acc = fmaf(q[c].y, kk.y, acc);
-                }
+    for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;    // rows g and g+8
+
+    for (int k0 = 0; k0 < T; k0 += ATT_BK) {
+        __syncthreads();
+        for (int i = tid; i < ATT_BK * (ATT_HD / 8); i += 128) {
+            const int r = i / (ATT_HD / 8), c8 = i % (ATT_HD / 8);
+            uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+            if (k0 + r < T) {
+                kv = *reinterpret_cast<const uint4*>(base + (size_t)(k0 + r) * 3 * d + d + c8 * 8);
+                vv = *reinterpret_cast<const uint4*>(base + (size_t)(k0 + r) * 3 * d + 2 * d + c8 * 8);
             }
-            s[jj] = acc;
-            mx = fmaxf(mx, acc);
+            *reinterpret_cast<uint4*>(Ks + r * ATT_LD + c8 * 8) = kv;
+            *reinterpret_cast<uint4*>(Vs + r * ATT_LD + c8 * 8) = vv;
         }
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float sum = 0.f;
+        __syncthreads();
+        // S = Q . K^T : 8 n-tiles of 8 keys
+        float s[8][4];
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) {
-            const float p = (jj * 32 + lane < T) ? expf(s[jj] - mx) : 0.f;
-            s[jj] = p;
-            sum += p;
-        }
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float inv = 1.0f / sum;
-        float a0 = 0.f, a1 = 0.f;
+        for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) {
-            const int jmax = min(32, T - jj * 32);
-            for (int src = 0; src < jmax; ++src) {
-                const float p = __shfl_sync(0xffffffffu, s[jj], src);
-                const float2 vv = __half22float2(*reinterpret_cast<const __half2*>(Vs + (size_t)(jj * 32 + src) * HD + lane * 2));
-                a0 = fmaf(p, vv.x, a0);
-                a1 = fmaf(p, vv.y, a1);
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {     // two n-tiles per ldmatrix.x4
+                uint32_t bfr[4];
+                // matrices: (keys 16jp..+7, dims 16kk..+7), (same keys, dims +8), (keys +8, dims ..+7), (keys +8, dims +8)
+                ldmatrix_x4(bfr, Ks + (jp * 16 + (lane & 7) + ((lane >> 4) << 3)) * ATT_LD + kk * 16 + ((lane >> 3) & 1) * 8);
+                mma_16816(s[2 * jp], qf[kk], bfr[0], bfr[1]);
+                mma_16816(s[2 * jp + 1], qf[kk], bfr[2], bfr[3]);
             }
         }
-        *reinterpret_cast<__half2*>(out + ((size_t)img * T + r) * d + head * HD + lane * 2) = __floats2half2_rn(a0 * inv, a1 * inv);
+        // mask keys beyond T, online softmax
+        float mx0 = m0, mx1 = m1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int key = k0 + j * 8 + 2 * t4;
+            if (key >= T) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+            if (key + 1 >= T) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float c0 = expf(m0 - mx0), c1 = expf(m1 - mx1);     // 0 on the first block (m = -inf)
+        m0 = mx0; m1 = mx1;
+        float rs0 = 0.f, rs1 = 0.f;
+        uint32_t pf[8][2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float p0 = expf(s[j][0] - mx0), p1 = expf(s[j][1] - mx0), p2 = expf(s[j][2] - mx1), p3 = expf(s[j][3] - mx1);
+            rs0 += p0 + p1; rs1 += p2 + p3;
+            __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+            pf[j][0] = *reinterpret_cast<uint32_t*>(&h01);
+            pf[j][1] = *reinterpret_cast<uint32_t*>(&h23);
+            o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1;
+        }
+        l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
+        // O += P . V : k-steps of 16 keys, 8 n-tiles of 8 dims
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t af[4] = {pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1]};
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                uint32_t bfr[4];
+                // transposed 8x8 loads of V[keys][dims]: (keys 16kk..+7, dims 16jp..+7), (keys +8, same dims), (keys ..+7, dims +8), (keys +8, dims +8)
+                ldmatrix_x4_trans(bfr, Vs + (kk * 16 + (lane & 15)) * ATT_LD + jp * 16 + (lane >> 4) * 8);
+                mma_16816(o[2 * jp], af, bfr[0], bfr[1]);
+                mma_16816(o[2 * jp + 1], af, bfr[2], bfr[3]);
+            }
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int col = head * ATT_HD + j * 8 + 2 * t4;
+        if (r0 < T) *reinterpret_cast<__half2*>(out + ((size_t)img * T + r0) * d + col) = __floats2half2_rn(o[j][0] * i0, o[j][1] * i0);
+        if (r1 < T) *reinterpret_cast<__half2*>(out + ((size_t)img * T + r1) * d + col) = __floats2half2_rn(o[j][2] * i1, o[j][3] * i1);
     }
 }
 
@@ -219,7 +276,6 @@ extern "C" int d2r_clip_load(const d2r_clip_cfg* cfg, const float* const* W, int
     const int side = cfg->image_size / P;
     c->NP = side * side;
     c->T = c->NP + 1;
-    D2R_REQUIRE(c->T <= 32 * 19, "d2r_clip_load: at most 608 tokens are supported");
     const int K0 = 3 * P * P;
     c->Kp = (K0 + 63) / 64 * 64;
     const int mlp = cfg->mlp;
@@ -278,17 +334,9 @@ extern "C" int d2r_clip_load(const d2r_clip_cfg* cfg, const float* const* W, int
     return D2R_OK;
 }
 
-template <int NJ>
 static int launch_attention(const d2r_clip* c, int B, cudaStream_t stream) {
-    const int T = c->T, d = c->cfg.hidden;
-    const size_t smem = (size_t)T * 66 * 2 + (size_t)T * 64 * 2;
-    static size_t granted[16] = {0};   // the attribute is a limit: only ever raise it
-    if (smem > granted[c->device & 15]) {
-        D2R_CUDA(cudaFuncSetAttribute(k_attention<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        granted[c->device & 15] = smem;
-    }
-    dim3 grid(B, c->cfg.heads);
-    k_attention<NJ><<<grid, 128, smem, stream>>>(c->qkv, T, d, c->o);
+    dim3 grid((c->T + ATT_BQ - 1) / ATT_BQ, c->cfg.heads, B);
+    k_attention<<<grid, 128, 0, stream>>>(c->qkv, c->T, c->cfg.hidden, c->o);
     count_launch();
     return D2R_OK;
 }
@@ -313,11 +361,7 @@ extern "C" int d2r_clip_encode(d2r_clip* c, const void* patches_dev, int B, floa
         count_launch();
         rc = gemm_f16(c->h, d, y.w_qkv, d, M, 3 * d, d, y.b_qkv, GEMM_OUT_F16, c->qkv, 3 * d, stream);
         if (rc) return rc;
-        const int nj = (T + 31) / 32;
-        if (nj <= 2) rc = launch_attention<2>(c, B, stream);
-        else if (nj <= 7) rc = launch_attention<7>(c, B, stream);
-        else if (nj <= 9) rc = launch_attention<9>(c, B, stream);
-        else rc = launch_attention<19>(c, B, stream);
+        rc = launch_attention(c, B, stream);
         if (rc) return rc;
         rc = gemm_f16(c->o, d, y.w_o, d, M, d, d, y.b_o, GEMM_RESIDUAL_F32, c->x, d, stream);
         if (rc) return rc;

@@ -26,6 +26,13 @@ namespace d2r {
 constexpr int TILE_W = 16, TILE_H = 8, CTA = TILE_W * TILE_H;   // 128 threads = 128 rays
 constexpr int MARCH_ITER = 10000;                                // NGP src/testbed_nerf.cu:59
 
+struct RayEntry {      // one primary ray that found an occupied sample (k_classify -> k_march_tc)
+    uint32_t k;        // candidate
+    uint32_t idx;      // pixel index x + W*y
+    float t;           // ray parameter of the first occupied sample
+    float t_exit;      // exit of the occupied box
+};
+
 struct MarchParams {
     ModelDev M;
     const float2* dirs;
@@ -43,6 +50,9 @@ struct MarchParams {
     uint8_t* u8_out;               //                 [K,H,W,3]
     unsigned long long* n_samples;
     unsigned long long* prof;      // profiling counters {samples, primary rays owned, work items} or null
+    RayEntry* entries;             // hit list (tensor-core path)
+    uint32_t* n_entries;           //   number of entries (device)
+    uint32_t* entry_cursor;        //   consumption cursor (device)
 };
 
 // shared-memory plan (floats): fp32 copies of the fp16 MLP weights, row-major [out][in]
@@ -183,7 +193,7 @@ __global__ void __launch_bounds__(CTA, 3) k_march(const __grid_constant__ MarchP
                 r.t_exit = oc.y;
             }
         }
-        const float cone = M.cone;   // calc_cone_angle returns the constant (nerf_device.cuh:369-376)
+        const StepC cone = make_stepc(M.cone);   // calc_cone_angle returns the constant (nerf_device.cuh:369-376)
         // ---- advance_pos_nerf (testbed_nerf.cu:333-362) ----
         if (alive) {
             t = advance_n_steps(t, cone, ld_random_val0(idx * 786433u));
@@ -309,7 +319,7 @@ __global__ void k_candidate_bbox(int K, int W, int H, const Mat3x4* __restrict__
                                  const float* __restrict__ col_hi, const float* __restrict__ row_lo,
                                  const float* __restrict__ row_hi, const float occ_min_x, const float occ_min_y,
                                  const float occ_min_z, const float occ_max_x, const float occ_max_y, const float occ_max_z,
-                                 int seg_mode, int4* __restrict__ bbox, uint32_t* __restrict__ tiles) {
+                                 int /*unused*/, int4* __restrict__ bbox, uint32_t* __restrict__ tiles) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
     int x0 = 0, y0 = 0, x1 = W - 1, y1 = H - 1;
@@ -342,13 +352,7 @@ __global__ void k_candidate_bbox(int K, int W, int H, const Mat3x4* __restrict__
     }
     uint32_t n = 0;
     if (x1 >= x0 && y1 >= y0) {
-        if (seg_mode) {   // k_march_tc work items: bands of rows holding ~TC_SEG_PIXELS pixels
-            const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
-            const int seg_rows = max(1, (TC_SEG_PIXELS + bw - 1) / bw);
-            n = (uint32_t)((bh + seg_rows - 1) / seg_rows);
-        } else {
-            n = (uint32_t)((x1 - x0 + TILE_W) / TILE_W) * (uint32_t)((y1 - y0 + TILE_H) / TILE_H);
-        }
+        n = (uint32_t)((x1 - x0 + TILE_W) / TILE_W) * (uint32_t)((y1 - y0 + TILE_H) / TILE_H);
     }
     else { x0 = 0; y0 = 0; x1 = -1; y1 = -1; }
     bbox[k] = make_int4(x0, y0, x1, y1);
@@ -434,6 +438,7 @@ struct Scratch {   // per-device scratch reused across calls (grown on demand)
     uint32_t* counter = nullptr; int capK = 0;
     float* ranges = nullptr; int capWH = 0; const void* ranges_view = nullptr;
     uint8_t* bg_u8 = nullptr; size_t cap_bg = 0;
+    RayEntry* entries = nullptr; size_t cap_entries = 0; uint32_t* entry_counters = nullptr;
     int n_sm = 0;
 };
 static Scratch g_scratch[16];
@@ -449,6 +454,7 @@ static int ensure_scratch(int device, int K, int W, int H) {
         s.capK = K;
     }
     if (!s.counter) D2R_CUDA(cudaMalloc(&s.counter, sizeof(uint32_t)));
+    if (!s.entry_counters) D2R_CUDA(cudaMalloc(&s.entry_counters, 2 * sizeof(uint32_t)));
     if (W + H > s.capWH) {
         cudaFree(s.ranges);
         D2R_CUDA(cudaMalloc(&s.ranges, (size_t)2 * (W + H) * sizeof(float)));
@@ -496,7 +502,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     // D2R_MARCH=simt selects the round-1 CUDA-core kernel (kept for A/B measurements); default: tensor-core kernel
     static const bool use_tc = []() { const char* e = getenv("D2R_MARCH"); return !(e && strcmp(e, "simt") == 0); }();
     k_candidate_bbox<<<(K + 127) / 128, 128, 0, stream>>>(K, W, H, s.cams, col_lo, col_hi, row_lo, row_hi, M.occ_min[0], M.occ_min[1],
-                                                          M.occ_min[2], M.occ_max[0], M.occ_max[1], M.occ_max[2], use_tc ? 1 : 0, s.bbox, s.tiles);
+                                                          M.occ_min[2], M.occ_max[0], M.occ_max[1], M.occ_max[2], 0, s.bbox, s.tiles);
     k_tile_prefix<<<1, 1024, 0, stream>>>(K, s.tiles, s.prefix, s.counter);
     count_launch(2);
 
@@ -520,6 +526,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     for (int i = 0; i < 4; ++i) P.bg[i] = bg[i];
     P.rgba_out = (float4*)rgba_out; P.depth_out = (float4*)depth_out; P.bg_rgba = (const float4*)bg_rgba; P.bg_depth = bg_depth;
     P.u8_out = u8_out; P.n_samples = n_samples;
+    P.entries = nullptr; P.n_entries = nullptr; P.entry_cursor = nullptr;
     static bool attr_set[16] = {false};
     if (!attr_set[m->device]) {
         D2R_CUDA(cudaFuncSetAttribute(k_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -539,8 +546,28 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
         evp = &pf.ev[pf.used++];
         D2R_CUDA(cudaEventRecord(evp->first, stream));
     }
-    if (use_tc) k_march_tc<<<s.n_sm * 4, TC_THREADS, TS_TOTAL, stream>>>(P);
-    else k_march<<<s.n_sm * 3, CTA, SMEM_BYTES, stream>>>(P);
+    if (use_tc) {
+        // pass 1 needs the tile count on the host (grid size, hit-list capacity): one 4-byte read-back
+        uint32_t total_tiles = 0;
+        D2R_CUDA(cudaMemcpyAsync(&total_tiles, s.prefix + K, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        D2R_CUDA(cudaStreamSynchronize(stream));
+        const size_t need = (size_t)total_tiles * CTA;
+        if (need > s.cap_entries) {
+            if (s.entries) D2R_CUDA(cudaFree(s.entries));
+            D2R_CUDA(cudaMalloc(&s.entries, need * sizeof(RayEntry)));
+            s.cap_entries = need;
+        }
+        D2R_CUDA(cudaMemsetAsync(s.entry_counters, 0, 2 * sizeof(uint32_t), stream));
+        P.entries = s.entries; P.n_entries = s.entry_counters; P.entry_cursor = s.entry_counters + 1;
+        if (total_tiles) {
+            k_classify<<<total_tiles, CTA, 0, stream>>>(P);
+            count_launch();
+            if (evp) D2R_CUDA(cudaEventRecord(evp->first, stream));   // time the march kernel alone
+            k_march_tc<<<s.n_sm * 4, TC_THREADS, TS_TOTAL, stream>>>(P);
+        }
+    } else {
+        k_march<<<s.n_sm * 3, CTA, SMEM_BYTES, stream>>>(P);
+    }
     if (evp) D2R_CUDA(cudaEventRecord(evp->second, stream));
     count_launch();
     D2R_CUDA(cudaGetLastError());

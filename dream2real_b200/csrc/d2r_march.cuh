@@ -38,32 +38,38 @@ __device__ __forceinline__ float ld_random_val0(uint32_t seed) {
 }
 
 // ---- stepping space: NGP nerf_device.cuh:378-428 -------------------------------------------------
-__device__ __forceinline__ float to_stepping_space(float t, float cone_angle) {
-    if (cone_angle <= 1e-5f) return t / MIN_CONE_STEPSIZE();
-    float log1p_c = __logf(1.0f + cone_angle);
-    float a = (__logf(MIN_CONE_STEPSIZE()) - __logf(log1p_c)) / log1p_c;
-    float b = (__logf(MAX_CONE_STEPSIZE()) - __logf(log1p_c)) / log1p_c;
-    float at = __expf(a * log1p_c);
-    float bt = __expf(b * log1p_c);
-    if (t <= at) return (t - at) / MIN_CONE_STEPSIZE() + a;
-    else if (t <= bt) return __logf(t) / log1p_c;
-    else return (t - bt) / MAX_CONE_STEPSIZE() + b;
+// The reference recomputes log1p_c, a, b, at, bt inside every call; they depend on the cone angle
+// only, so they are evaluated once per thread here -- with the same instruction sequence, hence the
+// same values -- and carried in StepC.
+struct StepC {
+    float cone, log1p_c, a, b, at, bt;
+};
+__device__ __forceinline__ StepC make_stepc(float cone_angle) {
+    StepC c;
+    c.cone = cone_angle;
+    c.log1p_c = __logf(1.0f + cone_angle);
+    c.a = (__logf(MIN_CONE_STEPSIZE()) - __logf(c.log1p_c)) / c.log1p_c;
+    c.b = (__logf(MAX_CONE_STEPSIZE()) - __logf(c.log1p_c)) / c.log1p_c;
+    c.at = __expf(c.a * c.log1p_c);
+    c.bt = __expf(c.b * c.log1p_c);
+    return c;
 }
-__device__ __forceinline__ float from_stepping_space(float n, float cone_angle) {
-    if (cone_angle <= 1e-5f) return n * MIN_CONE_STEPSIZE();
-    float log1p_c = __logf(1.0f + cone_angle);
-    float a = (__logf(MIN_CONE_STEPSIZE()) - __logf(log1p_c)) / log1p_c;
-    float b = (__logf(MAX_CONE_STEPSIZE()) - __logf(log1p_c)) / log1p_c;
-    float at = __expf(a * log1p_c);
-    float bt = __expf(b * log1p_c);
-    if (n <= a) return (n - a) * MIN_CONE_STEPSIZE() + at;
-    else if (n <= b) return __expf(n * log1p_c);
-    else return (n - b) * MAX_CONE_STEPSIZE() + bt;
+__device__ __forceinline__ float to_stepping_space(float t, const StepC& c) {
+    if (c.cone <= 1e-5f) return t / MIN_CONE_STEPSIZE();
+    if (t <= c.at) return (t - c.at) / MIN_CONE_STEPSIZE() + c.a;
+    else if (t <= c.bt) return __logf(t) / c.log1p_c;
+    else return (t - c.bt) / MAX_CONE_STEPSIZE() + c.b;
 }
-__device__ __forceinline__ float advance_n_steps(float t, float cone_angle, float n) {
-    return from_stepping_space(to_stepping_space(t, cone_angle) + n, cone_angle);
+__device__ __forceinline__ float from_stepping_space(float n, const StepC& c) {
+    if (c.cone <= 1e-5f) return n * MIN_CONE_STEPSIZE();
+    if (n <= c.a) return (n - c.a) * MIN_CONE_STEPSIZE() + c.at;
+    else if (n <= c.b) return __expf(n * c.log1p_c);
+    else return (n - c.b) * MAX_CONE_STEPSIZE() + c.bt;
 }
-__device__ __forceinline__ float calc_dt(float t, float cone_angle) { return advance_n_steps(t, cone_angle, 1.0f) - t; }
+__device__ __forceinline__ float advance_n_steps(float t, const StepC& c, float n) {
+    return from_stepping_space(to_stepping_space(t, c) + n, c);
+}
+__device__ __forceinline__ float calc_dt(float t, const StepC& c) { return advance_n_steps(t, c, 1.0f) - t; }
 
 __device__ __forceinline__ float warp_dt(float dt) {      // nerf_device.cuh:306-309
     float max_stepsize = MIN_CONE_STEPSIZE() * (1 << 7);
@@ -114,7 +120,7 @@ __device__ __forceinline__ float distance_to_next_voxel(float px, float py, floa
     float t = fminf(fminf(tx, ty), tz);
     return fmaxf(t / res, 0.0f);
 }
-__device__ __forceinline__ float advance_to_next_voxel(float t, float cone, float px, float py, float pz, float dx, float dy,
+__device__ __forceinline__ float advance_to_next_voxel(float t, const StepC& cone, float px, float py, float pz, float dx, float dy,
                                                        float dz, float ix, float iy, float iz, uint32_t mip) {
     float res = scalbnf(128.0f, -(int)mip);
     float t_target = t + distance_to_next_voxel(px, py, pz, dx, dy, dz, ix, iy, iz, res);
@@ -140,7 +146,7 @@ __device__ __forceinline__ bool raabb_contains(const ModelDev& M, float px, floa
 }
 
 // if_unoccupied_advance_to_next_occupied_voxel<false>, min_mip = 0
-__device__ __forceinline__ float skip_to_occupied(float t, float cone, const RayGeom& r, const ModelDev& M) {
+__device__ __forceinline__ float skip_to_occupied(float t, const StepC& cone, const RayGeom& r, const ModelDev& M) {
     const uint32_t max_mip = (uint32_t)M.max_cascade;
     while (true) {
         const float px = r.ox + t * r.dx, py = r.oy + t * r.dy, pz = r.oz + t * r.dz;
@@ -161,7 +167,7 @@ __device__ __forceinline__ float skip_to_occupied(float t, float cone, const Ray
 // samples -- does not depend on where along the empty prefix the walk starts.  We restart it one
 // lattice step before the box instead of walking ~50 voxels from the camera (values agree with the
 // reference's walk up to the rounding of the to/from_stepping_space round trip).
-__device__ __forceinline__ float fast_forward_to_box(float t, float cone, float t_box_entry) {
+__device__ __forceinline__ float fast_forward_to_box(float t, const StepC& cone, float t_box_entry) {
     if (t_box_entry > t) {
         const float s0 = to_stepping_space(t, cone), s1 = to_stepping_space(t_box_entry, cone);
         const float n = floorf(s1 - s0) - 1.0f;

@@ -10,16 +10,16 @@
 // the K-major B operand, fp32 accumulators in TMEM; every slot reads its own row back with tcgen05.ld
 // (lane == thread), applies ReLU, rounds to fp16 (the reference keeps fp16 activations, TCNN
 // fully_fused_mlp.cu:47-129) and writes the next layer's A row.  Compositing stays in registers.
-// Slots whose ray finished pull the next pixel of the CTA's work item from a shared cursor, so the
-// tile stays dense without any global-memory ray state or host round trip (the reference compacts
-// through global memory and syncs with the host every round, NGP testbed_nerf.cu:1664-1748).
+// Slots whose ray finished pull the next entry of the global hit list (written by k_classify, which
+// generates the rays, applies the Sobol jitter and walks each one to its first occupied sample), so the
+// tile stays dense without per-round global-memory compaction or host round trips (the reference
+// compacts through global memory and syncs with the host every round, NGP testbed_nerf.cu:1664-1748).
 #pragma once
 
 namespace d2r {
 
 constexpr int TC_THREADS = 128;
-constexpr int TC_SEG_PIXELS = 8192;       // target pixels per work item (a band of rows of one candidate's rectangle)
-constexpr int TC_REFILL_TRIES = 4;
+constexpr int TC_CHUNK = 256;             // hit-list entries a CTA claims at a time
 
 // shared memory plan (bytes); UMMA operand tiles want 16-byte alignment without swizzle, we give them 128
 constexpr int TS_WD0 = 0;                  // [64 x 32]  fp16, SBO 512
@@ -70,10 +70,87 @@ struct TcRay {
     RayGeom g;
     float t;
     float cr, cg, cb, cd, ca;
-    uint32_t idx;
+    float fwx, fwy, fwz;  // camera forward axis of this slot's candidate (depth compositing)
+    uint32_t idx, k;
     int n_steps;
     uint32_t sh[8];      // 16 fp16 SH coefficients
 };
+
+// primary-ray set-up shared by k_classify and the slot refill: init_rays_with_payload_kernel_nerf
+// (NGP testbed_nerf.cu:1394-1482).  Returns false when the ray can never take a sample.
+__device__ __forceinline__ bool setup_ray(const ModelDev& M, const Mat3x4& C, float2 dc, RayGeom& r, float& t, float& t_box) {
+    float vx = 0.f, vy = 0.f, vz = 0.f;   // mat3(camera) * (dc.x, dc.y, 1): tcnn accumulates column by column
+    vx += C.c[0][0] * dc.x; vy += C.c[0][1] * dc.x; vz += C.c[0][2] * dc.x;
+    vx += C.c[1][0] * dc.y; vy += C.c[1][1] * dc.y; vz += C.c[1][2] * dc.y;
+    vx += C.c[2][0] * 1.0f; vy += C.c[2][1] * 1.0f; vz += C.c[2][2] * 1.0f;
+    float len2 = 0.f;
+    len2 += vx * vx; len2 += vy * vy; len2 += vz * vz;
+    const float len = sqrtf(len2);
+    r.dx = vx / len; r.dy = vy / len; r.dz = vz / len;
+    r.ox = C.c[3][0]; r.oy = C.c[3][1]; r.oz = C.c[3][2];
+    r.ix = 1.0f / r.dx; r.iy = 1.0f / r.dy; r.iz = 1.0f / r.dz;
+    float lox = r.ox, loy = r.oy, loz = r.oz, ldx = r.dx, ldy = r.dy, ldz = r.dz;
+    if (!M.r2l_identity) {
+        lox = M.r2l[0] * r.ox + M.r2l[1] * r.oy + M.r2l[2] * r.oz;
+        loy = M.r2l[3] * r.ox + M.r2l[4] * r.oy + M.r2l[5] * r.oz;
+        loz = M.r2l[6] * r.ox + M.r2l[7] * r.oy + M.r2l[8] * r.oz;
+        ldx = M.r2l[0] * r.dx + M.r2l[1] * r.dy + M.r2l[2] * r.dz;
+        ldy = M.r2l[3] * r.dx + M.r2l[4] * r.dy + M.r2l[5] * r.dz;
+        ldz = M.r2l[6] * r.dx + M.r2l[7] * r.dy + M.r2l[8] * r.dz;
+    }
+    t = fmaxf(box_ray_intersect(M.raabb_min, M.raabb_max, lox, loy, loz, ldx, ldy, ldz).x, 0.0f) + 1e-6f;
+    if (!raabb_contains(M, r.ox + t * r.dx, r.oy + t * r.dy, r.oz + t * r.dz)) return false;
+    // rays that miss the box around all occupied cells can never take a sample
+    const float2 oc = box_ray_intersect(M.occ_min, M.occ_max, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
+    if (oc.x > 1e37f || oc.y < 0.f) return false;
+    t_box = oc.x;
+    r.t_exit = oc.y;
+    return true;
+}
+
+// Pass 1: one thread per pixel of every candidate's screen rectangle (16x8 tiles).  Generates the ray,
+// applies the Sobol start jitter (advance_pos_nerf, testbed_nerf.cu:333-362) and walks it to its first
+// occupied sample.  Rays that find one are appended (warp-aggregated) to the hit list; all others leave
+// their pixel as the fill kernel wrote it (the background).
+__global__ void __launch_bounds__(128) k_classify(const __grid_constant__ MarchParams P) {
+    const ModelDev& M = P.M;
+    const int tid = threadIdx.x;
+    const uint32_t tile = blockIdx.x;
+    int lo = 0, hi = P.K;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (P.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
+    }
+    const int k = lo;
+    const int4 bb = P.bbox[k];
+    const uint32_t local = tile - P.tile_prefix[k];
+    const int tiles_x = (bb.z - bb.x + TILE_W) / TILE_W;
+    const int x = bb.x + (int)(local % tiles_x) * TILE_W + (tid % TILE_W);
+    const int y = bb.y + (int)(local / tiles_x) * TILE_H + (tid / TILE_W);
+    bool hit = false;
+    RayEntry e;
+    if (x <= bb.z && y <= bb.w) {
+        const uint32_t idx = (uint32_t)x + (uint32_t)P.W * (uint32_t)y;
+        const Mat3x4 C = P.cams[k];
+        RayGeom r;
+        float t, t_box;
+        if (setup_ray(M, C, __ldg(P.dirs + idx), r, t, t_box)) {
+            const StepC cone = make_stepc(M.cone);
+            t = advance_n_steps(t, cone, ld_random_val0(idx * 786433u));
+            t = fast_forward_to_box(t, cone, t_box);
+            t = skip_to_occupied(t, cone, r, M);
+            if (t < MAX_DEPTH()) { hit = true; e.k = (uint32_t)k; e.idx = idx; e.t = t; e.t_exit = r.t_exit; }
+        }
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+    if (mask) {
+        const int lane = tid & 31, leader = __ffs(mask) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(P.n_entries, (uint32_t)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (hit) P.entries[base + __popc(mask & ((1u << lane) - 1))] = e;
+    }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constant__ MarchParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -82,15 +159,15 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constan
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + TS_MISC);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TS_MISC + 8);
     uint32_t* s_cursor = reinterpret_cast<uint32_t*>(smem + TS_MISC + 12);
-    uint32_t* s_item = reinterpret_cast<uint32_t*>(smem + TS_MISC + 16);
-    float* s_cam = reinterpret_cast<float*>(smem + TS_MISC + 32);   // 12 floats: 4 columns x 3
+    uint32_t* s_end = reinterpret_cast<uint32_t*>(smem + TS_MISC + 16);
+    uint32_t* s_done = reinterpret_cast<uint32_t*>(smem + TS_MISC + 20);
 
     stage_weights(smem + TS_WD0, M.w_d0, 64, 32, tid);
     stage_weights(smem + TS_WD1, M.w_d1, 16, 64, tid);
     stage_weights(smem + TS_WC0, M.w_c0, 64, 32, tid);
     stage_weights(smem + TS_WC1, M.w_c1, 64, 64, tid);
     stage_weights(smem + TS_WC2, M.w_c2, 16, 64, tid);
-    if (tid == 0) { mbar_init(mbar, 1); fence_barrier_init(); }
+    if (tid == 0) { mbar_init(mbar, 1); fence_barrier_init(); *s_cursor = 0; *s_end = 0; *s_done = 0; }
     if (warp == 0) tmem_alloc<128>(tmem_slot);
     fence_proxy_async();
     tc_fence_before();
@@ -104,109 +181,60 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constan
     unsigned char* rowA32 = smem + TS_A32 + umma_chunk_off(tid, 0, 32);
     unsigned char* rowA64 = smem + TS_A64 + umma_chunk_off(tid, 0, 64);
     uint32_t phase = 0;
-    const uint32_t total_items = P.tile_prefix[P.K];
-    const float cone = M.cone;
-    unsigned long long my_samples = 0, my_items = 0, my_rays = 0;
+    const uint32_t total_entries = *P.n_entries;
+    const StepC cone = make_stepc(M.cone);
+    unsigned long long my_samples = 0, my_rays = 0;
+    const size_t npx = (size_t)P.W * P.H;
 
-    while (true) {
-        __syncthreads();
-        if (tid == 0) *s_item = atomicAdd(P.counter, 1u);
-        __syncthreads();
-        const uint32_t item = *s_item;
-        if (item >= total_items) break;
-        int lo = 0, hi = P.K;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (P.tile_prefix[mid] <= item) lo = mid; else hi = mid;
-        }
-        const int k = lo;
-        const int4 bb = P.bbox[k];
-        const int bw = bb.z - bb.x + 1, bh = bb.w - bb.y + 1;
-        const int seg_rows = max(1, (TC_SEG_PIXELS + bw - 1) / bw);
-        const int ya = bb.y + (int)(item - P.tile_prefix[k]) * seg_rows;
-        const int yb = min(ya + seg_rows, bb.y + bh);
-        const uint32_t n_px = (uint32_t)bw * (uint32_t)(yb - ya);
-        if (tid < 12) s_cam[tid] = P.cams[k].c[tid / 3][tid % 3];
-        if (tid == 0) *s_cursor = 0;
-        __syncthreads();
-        const float fwx = s_cam[6], fwy = s_cam[7], fwz = s_cam[8];
-        const size_t frame = (size_t)k * P.W * P.H;
-        ++my_items;
+    bool alive = false;
+    TcRay R;
+    // finish a ray: keep rule, shade / tonemap background blend, outputs (same epilogue as k_march)
+    auto finish = [&](float cr, float cg, float cb, float cd, float ca, uint32_t idx, uint32_t k) {
+        if (!(ca > 0.001f)) { cr = cg = cb = cd = ca = 0.f; }
+        float4 shade = make_float4(srgb_to_linear_d(cr), srgb_to_linear_d(cg), srgb_to_linear_d(cb), ca);
+        float4 depth = make_float4(cd, cd, cd, ca);
+        const float w = (1.f - ca) * P.bg[3];
+        const float blr = srgb_to_linear_d(P.bg[0]), blg = srgb_to_linear_d(P.bg[1]), blb = srgb_to_linear_d(P.bg[2]);
+        shade.x += blr * w; shade.y += blg * w; shade.z += blb * w; shade.w += w;
+        depth.x += blr * w; depth.y += blg * w; depth.z += blb * w; depth.w += w;
+        const size_t o = (size_t)k * npx + idx;
+        if (P.rgba_out) P.rgba_out[o] = shade;
+        if (P.depth_out) P.depth_out[o] = depth;
+        if (P.u8_out) composite_pixel(shade, depth.x, __ldg(P.bg_rgba + idx), __ldg(P.bg_depth + idx), P.u8_out + o * 3);
+    };
 
-        bool alive = false;
-        TcRay R;
-        // finish a ray: keep rule, shade / tonemap background blend, outputs (same epilogue as k_march)
-        auto finish = [&](float cr, float cg, float cb, float cd, float ca, uint32_t idx) {
-            if (!(ca > 0.001f)) { cr = cg = cb = cd = ca = 0.f; }
-            float4 shade = make_float4(srgb_to_linear_d(cr), srgb_to_linear_d(cg), srgb_to_linear_d(cb), ca);
-            float4 depth = make_float4(cd, cd, cd, ca);
-            const float w = (1.f - ca) * P.bg[3];
-            const float blr = srgb_to_linear_d(P.bg[0]), blg = srgb_to_linear_d(P.bg[1]), blb = srgb_to_linear_d(P.bg[2]);
-            shade.x += blr * w; shade.y += blg * w; shade.z += blb * w; shade.w += w;
-            depth.x += blr * w; depth.y += blg * w; depth.z += blb * w; depth.w += w;
-            const size_t o = frame + idx;
-            if (P.rgba_out) P.rgba_out[o] = shade;
-            if (P.depth_out) P.depth_out[o] = depth;
-            if (P.u8_out) composite_pixel(shade, depth.x, __ldg(P.bg_rgba + idx), __ldg(P.bg_depth + idx), P.u8_out + o * 3);
-        };
-
+    {
         while (true) {
-            // ---- A. refill empty slots from the work item's pixel cursor ----
-            for (int tries = 0; !alive && tries < TC_REFILL_TRIES; ++tries) {
-                const uint32_t p = atomicAdd(s_cursor, 1u);
-                if (p >= n_px) break;
-                ++my_rays;
-                const int x = bb.x + (int)(p % (uint32_t)bw), y = ya + (int)(p / (uint32_t)bw);
-                const uint32_t idx = (uint32_t)x + (uint32_t)P.W * (uint32_t)y;
-                // init_rays_with_payload_kernel_nerf (NGP testbed_nerf.cu:1394-1482)
-                const float2 dc = __ldg(P.dirs + idx);
-                RayGeom r;
-                float vx = 0.f, vy = 0.f, vz = 0.f;
-                vx += s_cam[0] * dc.x; vy += s_cam[1] * dc.x; vz += s_cam[2] * dc.x;
-                vx += s_cam[3] * dc.y; vy += s_cam[4] * dc.y; vz += s_cam[5] * dc.y;
-                vx += s_cam[6] * 1.0f; vy += s_cam[7] * 1.0f; vz += s_cam[8] * 1.0f;
-                float len2 = 0.f;
-                len2 += vx * vx; len2 += vy * vy; len2 += vz * vz;
-                const float len = sqrtf(len2);
-                r.dx = vx / len; r.dy = vy / len; r.dz = vz / len;
-                r.ox = s_cam[9]; r.oy = s_cam[10]; r.oz = s_cam[11];
-                r.ix = 1.0f / r.dx; r.iy = 1.0f / r.dy; r.iz = 1.0f / r.dz;
-                float lox = r.ox, loy = r.oy, loz = r.oz, ldx = r.dx, ldy = r.dy, ldz = r.dz;
-                if (!M.r2l_identity) {
-                    lox = M.r2l[0] * r.ox + M.r2l[1] * r.oy + M.r2l[2] * r.oz;
-                    loy = M.r2l[3] * r.ox + M.r2l[4] * r.oy + M.r2l[5] * r.oz;
-                    loz = M.r2l[6] * r.ox + M.r2l[7] * r.oy + M.r2l[8] * r.oz;
-                    ldx = M.r2l[0] * r.dx + M.r2l[1] * r.dy + M.r2l[2] * r.dz;
-                    ldy = M.r2l[3] * r.dx + M.r2l[4] * r.dy + M.r2l[5] * r.dz;
-                    ldz = M.r2l[6] * r.dx + M.r2l[7] * r.dy + M.r2l[8] * r.dz;
-                }
-                float t = fmaxf(box_ray_intersect(M.raabb_min, M.raabb_max, lox, loy, loz, ldx, ldy, ldz).x, 0.0f) + 1e-6f;
-                bool ok = raabb_contains(M, r.ox + t * r.dx, r.oy + t * r.dy, r.oz + t * r.dz);
-                float t_box = 0.f;
-                if (ok) {
-                    const float2 oc = box_ray_intersect(M.occ_min, M.occ_max, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
-                    if (oc.x > 1e37f || oc.y < 0.f) ok = false;
-                    t_box = oc.x;
-                r.t_exit = oc.y;
-                }
-                if (ok) {   // advance_pos_nerf (testbed_nerf.cu:333-362)
-                    t = advance_n_steps(t, cone, ld_random_val0(idx * 786433u));
-                    t = fast_forward_to_box(t, cone, t_box);
-                    t = skip_to_occupied(t, cone, r, M);
-                    if (t >= MAX_DEPTH()) ok = false;
-                }
-                if (!ok) { finish(0.f, 0.f, 0.f, 0.f, 0.f, idx); continue; }
-                R.g = r; R.t = t; R.idx = idx; R.n_steps = 0;
-                R.cr = R.cg = R.cb = R.cd = R.ca = 0.f;
-                float sh[16];
-                const float wx = (r.dx + 1.0f) * 0.5f, wy = (r.dy + 1.0f) * 0.5f, wz = (r.dz + 1.0f) * 0.5f;
-                sh_enc4(wx * 2.f - 1.f, wy * 2.f - 1.f, wz * 2.f - 1.f, sh);
+            // ---- A. claim hit-list entries: thread 0 fetches a new chunk when the current one is used up ----
+            if (tid == 0 && *s_cursor >= *s_end && !*s_done) {
+                const uint32_t base = atomicAdd(P.entry_cursor, (uint32_t)TC_CHUNK);
+                if (base >= total_entries) { *s_done = 1; }
+                else { *s_cursor = base; *s_end = min(base + (uint32_t)TC_CHUNK, total_entries); }
+            }
+            __syncthreads();
+            const bool done = *s_done != 0;   // stable until every thread has passed this round's second barrier
+            if (!alive) {
+                const uint32_t i = atomicAdd(s_cursor, 1u);
+                if (i < *s_end) {
+                    const RayEntry e = P.entries[i];
+                    const Mat3x4 C = P.cams[e.k];
+                    float t0, t_box;
+                    setup_ray(M, C, __ldg(P.dirs + e.idx), R.g, t0, t_box);   // same arithmetic as pass 1
+                    R.g.t_exit = e.t_exit;
+                    R.t = e.t; R.idx = e.idx; R.k = e.k; R.n_steps = 0;
+                    R.fwx = C.c[2][0]; R.fwy = C.c[2][1]; R.fwz = C.c[2][2];
+                    R.cr = R.cg = R.cb = R.cd = R.ca = 0.f;
+                    float sh[16];
+                    const float wx = (R.g.dx + 1.0f) * 0.5f, wy = (R.g.dy + 1.0f) * 0.5f, wz = (R.g.dz + 1.0f) * 0.5f;
+                    sh_enc4(wx * 2.f - 1.f, wy * 2.f - 1.f, wz * 2.f - 1.f, sh);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    __half2 h = __floats2half2_rn(sh[2 * i], sh[2 * i + 1]);
-                    R.sh[i] = *reinterpret_cast<uint32_t*>(&h);
+                    for (int j = 0; j < 8; ++j) {
+                        __half2 h = __floats2half2_rn(sh[2 * j], sh[2 * j + 1]);
+                        R.sh[j] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    alive = true;
+                    ++my_rays;
                 }
-                alive = true;
             }
             // ---- B. next sample position + hash-grid features -> A row ----
             bool has_sample = false;
@@ -214,7 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constan
             if (alive) {
                 const float t = skip_to_occupied(R.t, cone, R.g, M);     // generate_next_nerf_network_inputs (:454-467)
                 if (t >= MAX_DEPTH()) {
-                    finish(R.cr, R.cg, R.cb, R.cd, R.ca, R.idx);
+                    finish(R.cr, R.cg, R.cb, R.cd, R.ca, R.idx, R.k);
                     alive = false;
                 } else {
                     const float dt = calc_dt(t, cone);
@@ -241,9 +269,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constan
             fence_proxy_async();
             tc_fence_before();
             if (!__syncthreads_or(has_sample ? 1 : 0)) {
-                const uint32_t cur = *s_cursor;
-                __syncthreads();
-                if (cur >= n_px) break;
+                if (done) break;
                 continue;
             }
             // ---- C. density layer 0: 32 -> 64, ReLU ----
@@ -342,15 +368,15 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constan
                 const float weight = alpha * T;
                 const float rr = logistic_d(raw0), gg = logistic_d(raw1), bb_ = logistic_d(raw2);
                 float dep = 0.f;
-                dep += fwx * (ux - R.g.ox); dep += fwy * (uy - R.g.oy); dep += fwz * (uz - R.g.oz);
+                dep += R.fwx * (ux - R.g.ox); dep += R.fwy * (uy - R.g.oy); dep += R.fwz * (uz - R.g.oz);
                 dep *= M.depth_scale;
                 R.cr += rr * weight; R.cg += gg * weight; R.cb += bb_ * weight; R.cd += dep * weight; R.ca += weight;
                 if (R.ca > (1.0f - M.min_transmittance)) {
                     R.cr /= R.ca; R.cg /= R.ca; R.cb /= R.ca; R.cd /= R.ca; R.ca /= R.ca;
-                    finish(R.cr, R.cg, R.cb, R.cd, R.ca, R.idx);
+                    finish(R.cr, R.cg, R.cb, R.cd, R.ca, R.idx, R.k);
                     alive = false;
                 } else if (++R.n_steps >= MARCH_ITER - 1) {
-                    finish(0.f, 0.f, 0.f, 0.f, 0.f, R.idx);       // never reaches the hit buffer in the reference
+                    finish(0.f, 0.f, 0.f, 0.f, 0.f, R.idx, R.k);  // never reaches the hit buffer in the reference
                     alive = false;
                 }
             }
@@ -367,7 +393,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constan
             if (P.prof && my_samples) atomicAdd(P.prof, my_samples);
             if (P.prof && my_rays) atomicAdd(P.prof + 1, my_rays);
         }
-        if (P.prof && tid == 0 && my_items) atomicAdd(P.prof + 2, my_items);
+
     }
 }
 
