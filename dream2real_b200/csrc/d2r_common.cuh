@@ -51,6 +51,7 @@ struct ModelDev {
     uint32_t level_offset[MAX_LEVELS + 1];
     float level_scale[MAX_LEVELS];
     uint32_t level_res[MAX_LEVELS];
+    uint32_t level_hashed[MAX_LEVELS];   // 1: coherent-prime hash into a 2^k table, 0: dense (wrap-around) index
     // MLP weights, fp16 row-major [out,in]
     const __half* w_d0;  // [64,32]
     const __half* w_d1;  // [16,64]

@@ -8,7 +8,8 @@
 //   warp 1      MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16
 //                              (M=128, N=BN, K=16) x4 per 64-wide k block; accumulator in TMEM;
 //                              tcgen05.commit releases smem stages / publishes the accumulator
-//   warps 2..5  epilogue     : tcgen05.ld (32 lanes x 32 columns) -> bias / quick-GELU / residual ->
+//   warps 2..9  epilogue     : two warps per TMEM lane quadrant (each half of the columns): tcgen05.ld
+//                              (32 lanes x 32 columns) -> bias / quick-GELU / residual ->
 //                              global stores
 // Used for every dense contraction of the CLIP vision tower (reference clip_scoring.py:180-181 ->
 // transformers CLIPModel.forward -> nn.Linear / patch-embedding conv).
@@ -23,7 +24,7 @@
 
 namespace d2r {
 
-constexpr int BM = 128, BK = 64, GEMM_THREADS = 192;
+constexpr int BM = 128, BK = 64, GEMM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 
 template <int BN>
 struct GemmSmem {
@@ -72,7 +73,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CU
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
@@ -122,6 +123,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CU
     } else {
         // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
         const int q = warp & 3;
+        const int chalf = (warp - 2) >> 2;     // 0: columns [0, BN/2), 1: [BN/2, BN)
         uint32_t tile_it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
@@ -130,7 +132,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CU
             mbar_wait(&tmem_full_bar[acc], (tile_it >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
                 tmem_ld_wait();

@@ -196,16 +196,14 @@ __device__ __forceinline__ float2 box_ray_intersect(const float* mn, const float
 }
 
 // ---- hash-grid encoding: TCNN grid.h:47-165, common_device.h:697-713, 826-838 --------------------
-__device__ __forceinline__ uint32_t grid_index(uint32_t hashmap_size, uint32_t res, uint32_t x, uint32_t y, uint32_t z) {
-    uint32_t stride = 1, index = 0;
-    // dim 0
-    if (stride <= hashmap_size) { index += x * stride; stride *= res; }
-    if (stride <= hashmap_size) { index += y * stride; stride *= res; }
-    if (stride <= hashmap_size) { index += z * stride; stride *= res; }
-    if (hashmap_size < stride) index = (x * 1u) ^ (y * 2654435761u) ^ (z * 805459861u);   // coherent_prime_hash
-    return index % hashmap_size;
-}
-
+// grid_index<3, CoherentPrime> restated without the runtime modulo.  Per level the host classifies it once
+// (d2r_model_load, same stride loop as the reference):
+//   hashed  <=> hashmap_size < res^3; then hashmap_size == 2^log2_hashmap_size, so `% size` is `& (size-1)`;
+//   dense   <=> index = x + y*res + z*res^2 with coordinates in [0, res] (the +0.5 offset lets a corner reach
+//               `res`: TCNN's "wraparound indexing in dense grids"), so index < 2*size and `% size` is one
+//               conditional subtract.
+// Same indices as the reference, an order of magnitude fewer instructions.
+//
 // one level -> 4 fp16 features (two half2).  The trilinear blend is an fp16 fma chain with the fp32
 // weight rounded to fp16 first: `result = fma((T)weight, grid_val(...), result)` (grid.h:144-165)
 __device__ __forceinline__ void encode_level(const ModelDev& M, int level, float x, float y, float z, __half2& f01, __half2& f23) {
@@ -225,10 +223,23 @@ __device__ __forceinline__ void encode_level(const ModelDev& M, int level, float
         pos[d] -= tmp;
     }
     uint2 v[8];
+    if (M.level_hashed[level]) {
+        const uint32_t mask = hashmap_size - 1;
+        const uint32_t hx[2] = {pg[0], pg[0] + 1u};
+        const uint32_t hy[2] = {pg[1] * 2654435761u, (pg[1] + 1u) * 2654435761u};
+        const uint32_t hz[2] = {pg[2] * 805459861u, (pg[2] + 1u) * 805459861u};
 #pragma unroll
-    for (int idx = 0; idx < 8; ++idx) {
-        const uint32_t cx = pg[0] + (idx & 1), cy = pg[1] + ((idx >> 1) & 1), cz = pg[2] + ((idx >> 2) & 1);
-        v[idx] = __ldg(table + grid_index(hashmap_size, res, cx, cy, cz));
+        for (int idx = 0; idx < 8; ++idx)
+            v[idx] = __ldg(table + ((hx[idx & 1] ^ hy[(idx >> 1) & 1] ^ hz[(idx >> 2) & 1]) & mask));
+    } else {
+        const uint32_t r2 = res * res;
+        const uint32_t base = pg[0] + pg[1] * res + pg[2] * r2;
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) {
+            uint32_t i = base + (idx & 1) + ((idx >> 1) & 1) * res + ((idx >> 2) & 1) * r2;
+            if (i >= hashmap_size) i -= hashmap_size;
+            v[idx] = __ldg(table + i);
+        }
     }
     __half2 r01 = __float2half2_rn(0.f), r23 = __float2half2_rn(0.f);
 #pragma unroll

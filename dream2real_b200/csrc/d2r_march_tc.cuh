@@ -152,6 +152,23 @@ __global__ void __launch_bounds__(128) k_classify(const __grid_constant__ MarchP
     }
 }
 
+// finish a ray: keep rule (a > 0.001), shade / tonemap background blend, outputs -- compact_kernel_nerf +
+// shade_kernel_nerf + tonemap_kernel (NGP testbed_nerf.cu:1302-1367, render_buffer.cu:529-561), then the
+// depth-test composite when a u8 frame is requested.  One out-of-line copy keeps the march loop small.
+__device__ __noinline__ void finish_ray(const MarchParams& P, float cr, float cg, float cb, float cd, float ca, uint32_t idx, uint32_t k) {
+    if (!(ca > 0.001f)) { cr = cg = cb = cd = ca = 0.f; }
+    float4 shade = make_float4(srgb_to_linear_d(cr), srgb_to_linear_d(cg), srgb_to_linear_d(cb), ca);
+    float4 depth = make_float4(cd, cd, cd, ca);
+    const float w = (1.f - ca) * P.bg[3];
+    const float blr = srgb_to_linear_d(P.bg[0]), blg = srgb_to_linear_d(P.bg[1]), blb = srgb_to_linear_d(P.bg[2]);
+    shade.x += blr * w; shade.y += blg * w; shade.z += blb * w; shade.w += w;
+    depth.x += blr * w; depth.y += blg * w; depth.z += blb * w; depth.w += w;
+    const size_t o = (size_t)k * ((size_t)P.W * P.H) + idx;
+    if (P.rgba_out) P.rgba_out[o] = shade;
+    if (P.depth_out) P.depth_out[o] = depth;
+    if (P.u8_out) composite_pixel(shade, depth.x, __ldg(P.bg_rgba + idx), __ldg(P.bg_depth + idx), P.u8_out + o * 3);
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constant__ MarchParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const ModelDev& M = P.M;
@@ -184,23 +201,11 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constan
     const uint32_t total_entries = *P.n_entries;
     const StepC cone = make_stepc(M.cone);
     unsigned long long my_samples = 0, my_rays = 0;
-    const size_t npx = (size_t)P.W * P.H;
 
     bool alive = false;
     TcRay R;
-    // finish a ray: keep rule, shade / tonemap background blend, outputs (same epilogue as k_march)
     auto finish = [&](float cr, float cg, float cb, float cd, float ca, uint32_t idx, uint32_t k) {
-        if (!(ca > 0.001f)) { cr = cg = cb = cd = ca = 0.f; }
-        float4 shade = make_float4(srgb_to_linear_d(cr), srgb_to_linear_d(cg), srgb_to_linear_d(cb), ca);
-        float4 depth = make_float4(cd, cd, cd, ca);
-        const float w = (1.f - ca) * P.bg[3];
-        const float blr = srgb_to_linear_d(P.bg[0]), blg = srgb_to_linear_d(P.bg[1]), blb = srgb_to_linear_d(P.bg[2]);
-        shade.x += blr * w; shade.y += blg * w; shade.z += blb * w; shade.w += w;
-        depth.x += blr * w; depth.y += blg * w; depth.z += blb * w; depth.w += w;
-        const size_t o = (size_t)k * npx + idx;
-        if (P.rgba_out) P.rgba_out[o] = shade;
-        if (P.depth_out) P.depth_out[o] = depth;
-        if (P.u8_out) composite_pixel(shade, depth.x, __ldg(P.bg_rgba + idx), __ldg(P.bg_depth + idx), P.u8_out + o * 3);
+        finish_ray(P, cr, cg, cb, cd, ca, idx, k);
     };
 
     {
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constan
                     R.t = t + dt;
                     has_sample = true;
                     ++my_samples;
-#pragma unroll
+#pragma unroll 1   // keep the kernel inside the instruction cache: 4 CTAs per SM sit at different PCs
                     for (int c = 0; c < 4; ++c) {
                         __half2 f0, f1, f2, f3;
                         encode_level(M, 2 * c, wpx, wpy, wpz, f0, f1);

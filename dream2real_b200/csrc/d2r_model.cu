@@ -213,6 +213,21 @@ extern "C" int d2r_model_load(const void* params_f16_host, size_t n_params, cons
     D2R_CUDA(cudaMemcpy(d.level_res, res_dev, MAX_LEVELS * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     cudaFree(scale_dev); cudaFree(res_dev);
     memcpy(d.level_offset, offsets, sizeof(offsets));
+    for (int l = 0; l < cfg->n_levels; ++l) {
+        // the reference's stride loop (tiny-cuda-nn common_device.h:697-713) decides dense vs hashed per level
+        const uint32_t size = offsets[l + 1] - offsets[l], res = d.level_res[l];
+        uint32_t stride = 1;
+        for (int dim = 0; dim < 3 && stride <= size; ++dim) stride *= res;
+        d.level_hashed[l] = size < stride ? 1u : 0u;
+        if (d.level_hashed[l] && (size & (size - 1)) != 0) {
+            set_error("d2r_model_load: hashed level with a non power-of-two table");
+            return D2R_ERR_INVALID;
+        }
+        if (!d.level_hashed[l] && (uint64_t)res * res * res + (uint64_t)res * res + res >= 2ull * size) {
+            set_error("d2r_model_load: dense level index range exceeds 2x the table size");
+            return D2R_ERR_INVALID;
+        }
+    }
 
     const __half* p = (const __half*)m->params_dev;
     d.w_d0 = p; p += 64 * 32;
