@@ -60,9 +60,8 @@ __device__ __forceinline__ void issue_layer(uint32_t a_addr, uint32_t b_addr, in
 }
 
 __device__ __forceinline__ uint32_t pack_relu_h2(uint32_t a, uint32_t b, bool relu) {
-    float x = __uint_as_float(a), y = __uint_as_float(b);
-    if (relu) { x = fmaxf(x, 0.f); y = fmaxf(y, 0.f); }
-    __half2 h = __floats2half2_rn(x, y);
+    __half2 h = __floats2half2_rn(__uint_as_float(a), __uint_as_float(b));
+    if (relu) h = __hmax2(h, __float2half2_rn(0.f));     // round-then-ReLU == ReLU-then-round, one op for two values
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
@@ -71,7 +70,7 @@ struct TcRay {
     float t;
     float cr, cg, cb, cd, ca;
     float fwx, fwy, fwz;  // camera forward axis of this slot's candidate (depth compositing)
-    uint32_t idx, k;
+    uint32_t ei;          // hit-list index of the ray in this slot
     int n_steps;
     uint32_t sh[8];      // 16 fp16 SH coefficients
 };
@@ -154,8 +153,8 @@ __global__ void __launch_bounds__(128) k_classify(const __grid_constant__ MarchP
 
 // finish a ray: keep rule (a > 0.001), shade / tonemap background blend, outputs -- compact_kernel_nerf +
 // shade_kernel_nerf + tonemap_kernel (NGP testbed_nerf.cu:1302-1367, render_buffer.cu:529-561), then the
-// depth-test composite when a u8 frame is requested.  One out-of-line copy keeps the march loop small.
-__device__ __noinline__ void finish_ray(const MarchParams& P, float cr, float cg, float cb, float cd, float ca, uint32_t idx, uint32_t k) {
+// depth-test composite when a u8 frame is requested.
+__device__ __forceinline__ void finish_ray(const MarchParams& P, float cr, float cg, float cb, float cd, float ca, uint32_t idx, uint32_t k) {
     if (!(ca > 0.001f)) { cr = cg = cb = cd = ca = 0.f; }
     float4 shade = make_float4(srgb_to_linear_d(cr), srgb_to_linear_d(cg), srgb_to_linear_d(cb), ca);
     float4 depth = make_float4(cd, cd, cd, ca);
@@ -167,6 +166,16 @@ __device__ __noinline__ void finish_ray(const MarchParams& P, float cr, float cg
     if (P.rgba_out) P.rgba_out[o] = shade;
     if (P.depth_out) P.depth_out[o] = depth;
     if (P.u8_out) composite_pixel(shade, depth.x, __ldg(P.bg_rgba + idx), __ldg(P.bg_depth + idx), P.u8_out + o * 3);
+}
+
+// Pass 3: one thread per hit-list entry, every lane busy.
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ MarchParams P) {
+    const uint32_t n = *P.n_entries;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const RayEntry e = P.entries[i];
+        const float4 c = P.res_rgbd[i];
+        finish_ray(P, c.x, c.y, c.z, c.w, P.res_a[i], e.idx, e.k);
+    }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constant__ MarchParams P) {
@@ -204,8 +213,12 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constan
 
     bool alive = false;
     TcRay R;
-    auto finish = [&](float cr, float cg, float cb, float cd, float ca, uint32_t idx, uint32_t k) {
-        finish_ray(P, cr, cg, cb, cd, ca, idx, k);
+    // a finished ray only parks its accumulators (20 B, slot = its hit-list index); k_finish turns them into
+    // pixels afterwards with every lane busy (inline, this epilogue ran with ~2 of 32 lanes active and cost
+    // 13 % of the kernel's issue slots)
+    auto finish = [&](float cr, float cg, float cb, float cd, float ca, uint32_t ei) {
+        P.res_rgbd[ei] = make_float4(cr, cg, cb, cd);
+        P.res_a[ei] = ca;
     };
 
     {
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constan
                     float t0, t_box;
                     setup_ray(M, C, __ldg(P.dirs + e.idx), R.g, t0, t_box);   // same arithmetic as pass 1
                     R.g.t_exit = e.t_exit;
-                    R.t = e.t; R.idx = e.idx; R.k = e.k; R.n_steps = 0;
+                    R.t = e.t; R.ei = i; R.n_steps = 0;
                     R.fwx = C.c[2][0]; R.fwy = C.c[2][1]; R.fwz = C.c[2][2];
                     R.cr = R.cg = R.cb = R.cd = R.ca = 0.f;
                     float sh[16];
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constan
             if (alive) {
                 const float t = skip_to_occupied(R.t, cone, R.g, M);     // generate_next_nerf_network_inputs (:454-467)
                 if (t >= MAX_DEPTH()) {
-                    finish(R.cr, R.cg, R.cb, R.cd, R.ca, R.idx, R.k);
+                    finish(R.cr, R.cg, R.cb, R.cd, R.ca, R.ei);
                     alive = false;
                 } else {
                     const float dt = calc_dt(t, cone);
@@ -378,10 +391,10 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc(const __grid_constan
                 R.cr += rr * weight; R.cg += gg * weight; R.cb += bb_ * weight; R.cd += dep * weight; R.ca += weight;
                 if (R.ca > (1.0f - M.min_transmittance)) {
                     R.cr /= R.ca; R.cg /= R.ca; R.cb /= R.ca; R.cd /= R.ca; R.ca /= R.ca;
-                    finish(R.cr, R.cg, R.cb, R.cd, R.ca, R.idx, R.k);
+                    finish(R.cr, R.cg, R.cb, R.cd, R.ca, R.ei);
                     alive = false;
                 } else if (++R.n_steps >= MARCH_ITER - 1) {
-                    finish(0.f, 0.f, 0.f, 0.f, 0.f, R.idx, R.k);  // never reaches the hit buffer in the reference
+                    finish(0.f, 0.f, 0.f, 0.f, 0.f, R.ei);        // never reaches the hit buffer in the reference
                     alive = false;
                 }
             }
