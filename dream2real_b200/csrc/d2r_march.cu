@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(CTA, 3) k_march(const __grid_constant__ MarchP
 
 }  // namespace d2r
 #include "d2r_march_tc.cuh"
+#include "d2r_march_tc2.cuh"
 namespace d2r {
 
 // ---- per-candidate screen rectangle + tile prefix ---------------------------------------------------
@@ -504,6 +505,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     const ModelDev& M = m->dev;
     // D2R_MARCH=simt selects the round-1 CUDA-core kernel (kept for A/B measurements); default: tensor-core kernel
     static const bool use_tc = []() { const char* e = getenv("D2R_MARCH"); return !(e && strcmp(e, "simt") == 0); }();
+    static const bool use_tc1 = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "tc1") == 0; }();   // one sample per round
     k_candidate_bbox<<<(K + 127) / 128, 128, 0, stream>>>(K, W, H, s.cams, col_lo, col_hi, row_lo, row_hi, M.occ_min[0], M.occ_min[1],
                                                           M.occ_min[2], M.occ_max[0], M.occ_max[1], M.occ_max[2], 0, s.bbox, s.tiles);
     k_tile_prefix<<<1, 1024, 0, stream>>>(K, s.tiles, s.prefix, s.counter);
@@ -534,6 +536,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     if (!attr_set[m->device]) {
         D2R_CUDA(cudaFuncSetAttribute(k_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         D2R_CUDA(cudaFuncSetAttribute(k_march_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_TOTAL));
+        D2R_CUDA(cudaFuncSetAttribute(k_march_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
         attr_set[m->device] = true;
     }
     Prof& pf = g_prof[m->device];
@@ -569,7 +572,8 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
             k_classify<<<total_tiles, CTA, 0, stream>>>(P);
             count_launch();
             if (evp) D2R_CUDA(cudaEventRecord(evp->first, stream));   // time the march kernel alone
-            k_march_tc<<<s.n_sm * 4, TC_THREADS, TS_TOTAL, stream>>>(P);
+            if (use_tc1) k_march_tc<<<s.n_sm * 4, TC_THREADS, TS_TOTAL, stream>>>(P);
+            else k_march_tc2<<<s.n_sm * 4, TC_THREADS, T2_TOTAL, stream>>>(P);
             if (evp) { D2R_CUDA(cudaEventRecord(evp->second, stream)); evp = nullptr; }
             k_finish<<<s.n_sm * 8, 256, 0, stream>>>(P);
             count_launch(2);

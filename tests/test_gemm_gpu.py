@@ -20,7 +20,8 @@ def _gemm(A, B, bias, mode, out):
     return out
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 64, 128), (256, 256, 768), (200, 2304, 768), (50 * 7 + 3, 768, 3072), (1, 512, 768)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 64, 128), (256, 256, 768), (200, 2304, 768), (50 * 7 + 3, 768, 3072), (1, 512, 768),
+                                   (38400 + 17, 256, 128), (25600, 768, 768)])   # the last two take the 256-wide tile path
 def test_gemm_plain_f32_out(M, N, K):
     import torch
     torch.manual_seed(M * 7 + N + K)

@@ -116,6 +116,12 @@ def test_clip_vit_b32_vs_hf():
     _clip_parity(make_hf_clip("ViT-B/32", seed=7, vocab_size=1000), K=4, seed=2, tol_cos=1e-4, tol_logit_rel=2e-3)
 
 
+def test_clip_vit_l14_336_vs_hf():
+    """the architecture the reference actually loads (clip_scoring.py:150): 577 tokens, 24 layers, 588 -> 640 padded patch K"""
+    from dream2real_b200.clip import make_hf_clip
+    _clip_parity(make_hf_clip("ViT-L/14-336", seed=11, vocab_size=1000), K=2, seed=3, tol_cos=1e-4, tol_logit_rel=2e-3)
+
+
 @pytest.fixture(scope="module")
 def scene(tmp_path_factory):
     from dream2real_b200 import synth
