@@ -148,12 +148,18 @@ def run_ours(args):
     scores = torch.empty(K, dtype=torch.float32, device=device)
     gathered = torch.empty(K * world, dtype=torch.float32, device=device) if world > 1 else None
 
+    vit_events = []      # (start, end) CUDA events around every ViT forward of the timed region
+
     def step_resident():
         for s in range(0, K, args.chunk):
             e = min(s + args.chunk, K)
             fg.render_composite_batch(cams_ngp[s:e], res, res, bg_image, bg_depth, out_u8=u8[: e - s], ngp_convention=True)
             patches, _ = cv.preprocess(u8[: e - s], rot90=True)
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
             emb = cv.encode_patches(patches, e - s)
+            ev[1].record()
+            vit_events.append(ev)
             scores[s:e] = cv.score(emb, txt, n_goal=1)
         if world > 1:
             dist.all_gather_into_tensor(gathered, scores)
@@ -161,16 +167,15 @@ def run_ours(args):
     pinned_poses = torch.from_numpy(valid_poses_ngp).pin_memory()
     host_scores = torch.empty(K, dtype=torch.float32).pin_memory()
 
+    from dream2real_b200.clip_scoring import score_renders
+
     def step_e2e():
-        """public API with HOST buffers: poses in pinned host memory -> scores back on the host."""
+        """public API with HOST buffers, the way optimise_pose_grid drives it: poses in pinned host memory ->
+        renderer.render (one call: background once, all candidates) -> score_renders -> scores back on the host."""
         vp = pinned_poses.numpy()
-        renders_done = 0
-        for s in range(0, K, args.chunk):
-            e = min(s + args.chunk, K)
-            out = rnd.render(vp[s:e], render_poses_ngp, [0], tm.depths[:1], tm.movable_masks, save=False, return_tensor=True)
-            emb = cv.encode_images(out, rot90=True)
-            scores[s:e] = cv.score(emb, txt, n_goal=1)
-            renders_done += e - s
+        out = rnd.render(vp, render_poses_ngp, [0], tm.depths[:1], tm.movable_masks, save=False, return_tensor=True)
+        scores.copy_(score_renders(out, cv, txt, n_goal=1))
+        del out
         if world > 1:
             dist.all_gather_into_tensor(gathered, scores)
         host_scores.copy_(scores, non_blocking=True)
@@ -201,7 +206,9 @@ def run_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    vit_events.clear()
     ms = timed(step_resident, args.steps)
+    vit_ms = sum(a.elapsed_time(b) for a, b in vit_events)
     clk = clocks.stop() if rank == 0 else None
     launches = N.launch_count()
     import ctypes as C
@@ -247,6 +254,18 @@ def run_ours(args):
                      "avg_launch_ms": mm.value / max(1, nl.value), "share_of_step": mm.value / ms,
                      "note": "algorithmic bytes; both hash tables (~50 MB) are L2-resident so DRAM traffic is far lower (DESIGN.md section 5)"},
     }
+    from dream2real_b200.clip import CLIP_CONFIGS
+    c = CLIP_CONFIGS[args.clip]
+    T = (c["image_size"] // c["patch_size"]) ** 2 + 1
+    kp = (3 * c["patch_size"] ** 2 + 63) // 64 * 64
+    d_, mlp_ = c["hidden"], c["mlp"]
+    vit_flop = (2.0 * (T - 1) * d_ * kp + c["layers"] * (8.0 * T * d_ * d_ + 4.0 * T * d_ * mlp_ + 4.0 * T * T * d_) + 2.0 * d_ * c["proj"])
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    vit_tf = vit_flop * K * args.steps / (vit_ms / 1e3) / 1e12 if vit_ms > 0 else 0.0
+    out["roofline_vit"] = {"kernel": "CLIP ViT forward (tcgen05 GEMMs + attention + LayerNorm)", "bound": "tensor", "achieved": vit_tf,
+                           "peak": tf_peak, "unit": "TFLOP/s", "frac": vit_tf / tf_peak,
+                           "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if "bf16_tflops_sustained" in peaks
+                           else "fallback (B200_PROFILING.md)", "gflop_per_image": vit_flop / 1e9, "share_of_step": vit_ms / ms}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, scene_dir, n=args.cpu_sample)
     try:

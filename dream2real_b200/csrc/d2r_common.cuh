@@ -52,6 +52,8 @@ struct ModelDev {
     float level_scale[MAX_LEVELS];
     uint32_t level_res[MAX_LEVELS];
     uint32_t level_hashed[MAX_LEVELS];   // 1: coherent-prime hash into a 2^k table, 0: dense (wrap-around) index
+    const uint2* level_table[MAX_LEVELS];   // grid + level_offset[l] as 8-byte entries: one IMAD.WIDE per corner address
+    uint32_t level_size[MAX_LEVELS];     // entries of the level; hashed levels: a power of two
     // MLP weights, fp16 row-major [out,in]
     const __half* w_d0;  // [64,32]
     const __half* w_d1;  // [16,64]

@@ -207,11 +207,9 @@ __device__ __forceinline__ float2 box_ray_intersect(const float* mn, const float
 // one level -> 4 fp16 features (two half2).  The trilinear blend is an fp16 fma chain with the fp32
 // weight rounded to fp16 first: `result = fma((T)weight, grid_val(...), result)` (grid.h:144-165)
 __device__ __forceinline__ void encode_level(const ModelDev& M, int level, float x, float y, float z, __half2& f01, __half2& f23) {
-    const uint32_t off = M.level_offset[level];
-    const uint32_t hashmap_size = M.level_offset[level + 1] - off;
+    const uint2* __restrict__ table = M.level_table[level];    // 64-bit base once per level, 32-bit entry index per corner
+    const uint32_t hashmap_size = M.level_size[level];
     const float scale = M.level_scale[level];
-    const uint32_t res = M.level_res[level];
-    const uint2* __restrict__ table = reinterpret_cast<const uint2*>(M.grid) + off;
     float pos[3];
     uint32_t pg[3];
     const float in[3] = {x, y, z};
@@ -232,6 +230,7 @@ __device__ __forceinline__ void encode_level(const ModelDev& M, int level, float
         for (int idx = 0; idx < 8; ++idx)
             v[idx] = __ldg(table + ((hx[idx & 1] ^ hy[(idx >> 1) & 1] ^ hz[(idx >> 2) & 1]) & mask));
     } else {
+        const uint32_t res = M.level_res[level];
         const uint32_t r2 = res * res;
         const uint32_t base = pg[0] + pg[1] * res + pg[2] * r2;
 #pragma unroll
@@ -256,6 +255,175 @@ __device__ __forceinline__ void encode_level(const ModelDev& M, int level, float
     }
     f01 = r01;
     f23 = r23;
+}
+
+// NL consecutive levels at once: all 8*NL gathers are issued before the first blend, so a thread keeps 8*NL loads
+// in flight instead of 8 (the per-level hashed/dense branch otherwise fences each level's loads off from the next's).
+// Same arithmetic per level as encode_level.
+template <int NL>
+__device__ __forceinline__ void encode_levels(const ModelDev& M, int level0, float x, float y, float z, __half2* f /* [2 * NL] */) {
+    uint32_t ei[NL][8];
+    float pos[NL][3];
+    const uint2* table[NL];
+    const float in[3] = {x, y, z};
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const int level = level0 + l;
+        table[l] = M.level_table[level];
+        const uint32_t hashmap_size = M.level_size[level];
+        const float scale = M.level_scale[level];
+        uint32_t pg[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {    // pos_fract
+            pos[l][d] = fmaf(scale, in[d], 0.5f);
+            float tmp = floorf(pos[l][d]);
+            pg[d] = (uint32_t)(int)tmp;
+            pos[l][d] -= tmp;
+        }
+        if (M.level_hashed[level]) {
+            const uint32_t mask = hashmap_size - 1;
+            const uint32_t hx[2] = {pg[0], pg[0] + 1u};
+            const uint32_t hy[2] = {pg[1] * 2654435761u, (pg[1] + 1u) * 2654435761u};
+            const uint32_t hz[2] = {pg[2] * 805459861u, (pg[2] + 1u) * 805459861u};
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) ei[l][idx] = (hx[idx & 1] ^ hy[(idx >> 1) & 1] ^ hz[(idx >> 2) & 1]) & mask;
+        } else {
+            const uint32_t res = M.level_res[level];
+            const uint32_t r2 = res * res;
+            const uint32_t base = pg[0] + pg[1] * res + pg[2] * r2;
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) {
+                uint32_t i = base + (idx & 1) + ((idx >> 1) & 1) * res + ((idx >> 2) & 1) * r2;
+                if (i >= hashmap_size) i -= hashmap_size;
+                ei[l][idx] = i;
+            }
+        }
+    }
+    uint2 v[NL][8];
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) v[l][idx] = __ldg(table[l] + ei[l][idx]);
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        __half2 r01 = __float2half2_rn(0.f), r23 = __float2half2_rn(0.f);
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) {
+            float weight = 1;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if ((idx & (1 << d)) == 0) weight *= 1 - pos[l][d];
+                else weight *= pos[l][d];
+            }
+            const __half2 w2 = __float2half2_rn(weight);
+            r01 = __hfma2(w2, *reinterpret_cast<const __half2*>(&v[l][idx].x), r01);
+            r23 = __hfma2(w2, *reinterpret_cast<const __half2*>(&v[l][idx].y), r23);
+        }
+        f[2 * l] = r01;
+        f[2 * l + 1] = r23;
+    }
+}
+
+// Lane-pair cooperative variant of encode_levels (the whole warp must call it, converged).
+// The gathers are bound by L1 tag work: a warp-wide load costs one pass per distinct 128-byte line it touches, and at
+// the fine levels every lane touches its own lines.  The two x-neighbours (x, x+1) of a corner pair sit in the same line
+// (dense: adjacent entries; hashed: the x term enters the coherent-prime hash un-multiplied, so idx(x+1) = idx(x) ^ (2^(t+1)-1),
+// t = trailing ones of x -- the same line 15 times out of 16), but one thread can only fetch them with two instructions.
+// So lanes 2j / 2j+1 share the work: instruction set 1 serves the even lane's sample (even lane loads the x corner, odd lane
+// the x+1 corner -> ONE line for the pair), set 2 serves the odd lane's sample, and a shuffle hands each lane the other
+// corner of its own sample.  Same number of loads, half the lines per instruction; the blend (order, rounding) is unchanged.
+template <int NL>
+__device__ __forceinline__ void encode_levels_pair(const ModelDev& M, int level0, float x, float y, float z, __half2* f /* [2 * NL] */) {
+    const uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t odd = (uint32_t)lane & 1u;
+    const int lane_e = lane & ~1, lane_o = lane | 1;
+    uint32_t e1[NL][4], e2[NL][4];
+    float pos[NL][3];
+    const uint2* table[NL];
+    const float in[3] = {x, y, z};
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const int level = level0 + l;
+        table[l] = M.level_table[level];
+        const uint32_t hashmap_size = M.level_size[level];
+        const float scale = M.level_scale[level];
+        uint32_t pa[3], pb[3];       // integer cell of the even lane's sample / of the odd lane's sample
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {    // pos_fract
+            pos[l][d] = fmaf(scale, in[d], 0.5f);
+            float tmp = floorf(pos[l][d]);
+            const uint32_t pg = (uint32_t)(int)tmp;
+            pos[l][d] -= tmp;
+            pa[d] = __shfl_sync(FULL, pg, lane_e);
+            pb[d] = __shfl_sync(FULL, pg, lane_o);
+        }
+        // set 1: this lane's corner of the even lane's sample has x offset `odd`; set 2 (odd lane's sample): offset `1 - odd`,
+        // so that in both sets the lane that OWNS the sample fetches the x corner and its partner the x+1 corner
+        const uint32_t xa = pa[0] + odd, xb = pb[0] + (odd ^ 1u);
+        if (M.level_hashed[level]) {
+            const uint32_t mask = hashmap_size - 1;
+            const uint32_t ya[2] = {pa[1] * 2654435761u, (pa[1] + 1u) * 2654435761u};
+            const uint32_t za[2] = {pa[2] * 805459861u, (pa[2] + 1u) * 805459861u};
+            const uint32_t yb[2] = {pb[1] * 2654435761u, (pb[1] + 1u) * 2654435761u};
+            const uint32_t zb[2] = {pb[2] * 805459861u, (pb[2] + 1u) * 805459861u};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                e1[l][k] = (xa ^ ya[k & 1] ^ za[k >> 1]) & mask;
+                e2[l][k] = (xb ^ yb[k & 1] ^ zb[k >> 1]) & mask;
+            }
+        } else {
+            const uint32_t res = M.level_res[level];
+            const uint32_t r2 = res * res;
+            const uint32_t ba = xa + pa[1] * res + pa[2] * r2, bb = xb + pb[1] * res + pb[2] * r2;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t i = ba + (k & 1) * res + (k >> 1) * r2;
+                if (i >= hashmap_size) i -= hashmap_size;
+                e1[l][k] = i;
+                uint32_t j = bb + (k & 1) * res + (k >> 1) * r2;
+                if (j >= hashmap_size) j -= hashmap_size;
+                e2[l][k] = j;
+            }
+        }
+    }
+    uint2 r1[NL][4], r2v[NL][4];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r1[l][k] = __ldg(table[l] + e1[l][k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r2v[l][k] = __ldg(table[l] + e2[l][k]);
+    }
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        __half2 r01 = __float2half2_rn(0.f), r23 = __float2half2_rn(0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // even lane: set 1 holds its own x corner, set 2 its partner's x+1 corner; odd lane: the other way round
+            uint2 mine, send, recv;
+            mine.x = odd ? r2v[l][k].x : r1[l][k].x; mine.y = odd ? r2v[l][k].y : r1[l][k].y;
+            send.x = odd ? r1[l][k].x : r2v[l][k].x; send.y = odd ? r1[l][k].y : r2v[l][k].y;
+            recv.x = __shfl_xor_sync(FULL, send.x, 1);
+            recv.y = __shfl_xor_sync(FULL, send.y, 1);
+#pragma unroll
+            for (int xb_ = 0; xb_ < 2; ++xb_) {     // corner idx = xb_ + 2 * k: x fastest, as in the reference's loop
+                const int idx = xb_ + 2 * k;
+                float weight = 1;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    if ((idx & (1 << d)) == 0) weight *= 1 - pos[l][d];
+                    else weight *= pos[l][d];
+                }
+                const __half2 w2 = __float2half2_rn(weight);
+                const uint2 v = xb_ ? recv : mine;
+                r01 = __hfma2(w2, *reinterpret_cast<const __half2*>(&v.x), r01);
+                r23 = __hfma2(w2, *reinterpret_cast<const __half2*>(&v.y), r23);
+            }
+        }
+        f[2 * l] = r01;
+        f[2 * l + 1] = r23;
+    }
 }
 
 // ---- spherical harmonics degree 4: TCNN common_device.h:340-365 ----------------------------------

@@ -27,6 +27,9 @@ constexpr int T2_TILE = 16384;
 constexpr int T2_MISC = T2_A64 + 2 * T2_TILE;
 constexpr int T2_TOTAL = T2_MISC + 256;
 
+// LPI = hash-grid levels gathered per loop iteration (8 loads each in flight together): 2 or 4
+// COOP = lane-pair cooperative gathers (encode_levels_pair)
+template <int LPI, bool COOP>
 __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc2(const __grid_constant__ MarchParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const ModelDev& M = P.M;
@@ -115,47 +118,68 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc2(const __grid_consta
             }
         }
         // ---- B. up to two sample positions + hash-grid features -> A rows of tile 0 / tile 1 ----
+        // One walk loop for both samples (generate_next_nerf_network_inputs, testbed_nerf.cu:454-467, twice): the same
+        // sequence of operations on t as two calls of if_unoccupied_advance_to_next_occupied_voxel, but lanes that need an
+        // empty-voxel step for sample 0 and lanes that need one for sample 1 take it in the same warp iteration.
         int n_s = 0;                               // samples prepared this round (0, 1 or 2)
         bool exits = false;                        // the ray leaves the occupied region after its last prepared sample
-        float wp[2][3], wdt[2];
-        wp[0][0] = wp[0][1] = wp[0][2] = wp[1][0] = wp[1][1] = wp[1][2] = 0.f; wdt[0] = wdt[1] = 0.f;
+        float wp0x = 0.f, wp0y = 0.f, wp0z = 0.f, wp1x = 0.f, wp1y = 0.f, wp1z = 0.f;
+        float dep0 = 0.f, dep1 = 0.f, dtu0 = 0.f, dtu1 = 0.f;     // what compositing needs of a sample: depth and unwarped dt
         if (alive) {
             float t = R.t;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (s == n_s && !exits) {
-                    t = skip_to_occupied(t, cone, R.g, M);           // generate_next_nerf_network_inputs (:454-467)
-                    if (t >= MAX_DEPTH()) {
-                        exits = true;
-                    } else {
-                        const float dt = calc_dt(t, cone);
-                        const float px = R.g.ox + R.g.dx * t, py = R.g.oy + R.g.dy * t, pz = R.g.oz + R.g.dz * t;
-                        wp[s][0] = (px - M.aabb_min[0]) / M.aabb_diag[0];
-                        wp[s][1] = (py - M.aabb_min[1]) / M.aabb_diag[1];
-                        wp[s][2] = (pz - M.aabb_min[2]) / M.aabb_diag[2];
-                        wdt[s] = warp_dt(dt);
-                        t += dt;
-                        n_s = s + 1;
-                    }
+            const uint32_t max_mip = (uint32_t)M.max_cascade;
+            while (true) {
+                const float px = R.g.ox + t * R.g.dx, py = R.g.oy + t * R.g.dy, pz = R.g.oz + t * R.g.dz;
+                if (t >= MAX_DEPTH() || t > R.g.t_exit || !raabb_contains(M, px, py, pz)) { exits = true; break; }
+                uint32_t mip = min(max(mip_from_pos(px, py, pz), 0u), max_mip);
+                if (density_grid_occupied_at(px, py, pz, M.bitfield, mip)) {
+                    const float dt = calc_dt(t, cone);
+                    const float wx = (px - M.aabb_min[0]) / M.aabb_diag[0];
+                    const float wy = (py - M.aabb_min[1]) / M.aabb_diag[1];
+                    const float wz = (pz - M.aabb_min[2]) / M.aabb_diag[2];
+                    // composite_kernel_nerf reads the position back from the network input (unwarp_position) and
+                    // the step from warp_dt/unwarp_dt: same arithmetic here, evaluated before the MLP instead of after
+                    const float ux = M.aabb_min[0] + wx * M.aabb_diag[0];
+                    const float uy = M.aabb_min[1] + wy * M.aabb_diag[1];
+                    const float uz = M.aabb_min[2] + wz * M.aabb_diag[2];
+                    float dep = 0.f;
+                    dep += R.fwx * (ux - R.g.ox); dep += R.fwy * (uy - R.g.oy); dep += R.fwz * (uz - R.g.oz);
+                    dep *= M.depth_scale;
+                    const float dtu = unwarp_dt(warp_dt(dt));
+                    if (n_s == 0) { wp0x = wx; wp0y = wy; wp0z = wz; dep0 = dep; dtu0 = dtu; }
+                    else { wp1x = wx; wp1y = wy; wp1z = wz; dep1 = dep; dtu1 = dtu; }
+                    t += dt;
+                    if (++n_s == 2) break;
+                    continue;
                 }
+                while (mip < max_mip && !density_grid_occupied_at(px, py, pz, M.bitfield, mip + 1)) ++mip;
+                t = advance_to_next_voxel(t, cone, px, py, pz, R.g.dx, R.g.dy, R.g.dz, R.g.ix, R.g.iy, R.g.iz, mip);
             }
             R.t = t;
             if (n_s == 0) {                         // nothing left to sample: the ray is finished as it stands
                 finish(R.cr, R.cg, R.cb, R.cd, R.ca, R.ei);
                 alive = false;
             }
+        }
+        // hash-grid features: warp-converged (the cooperative gather shuffles between lanes); lanes without a sample
+        // compute on the zero position and skip the store
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (s < n_s) {
+        for (int s = 0; s < 2; ++s) {
+            if (__any_sync(0xffffffffu, s < n_s)) {
+                const float sx = s ? wp1x : wp0x, sy = s ? wp1y : wp0y, sz = s ? wp1z : wp0z;
 #pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
-                        __half2 f0, f1, f2, f3;
-                        encode_level(M, 2 * c, wp[s][0], wp[s][1], wp[s][2], f0, f1);
-                        encode_level(M, 2 * c + 1, wp[s][0], wp[s][1], wp[s][2], f2, f3);
-                        uint4 v;
-                        v.x = *reinterpret_cast<uint32_t*>(&f0); v.y = *reinterpret_cast<uint32_t*>(&f1);
-                        v.z = *reinterpret_cast<uint32_t*>(&f2); v.w = *reinterpret_cast<uint32_t*>(&f3);
-                        *reinterpret_cast<uint4*>(rowA32 + s * T2_TILE + c * 128) = v;
+                for (int c = 0; c < 8 / LPI; ++c) {
+                    __half2 f[2 * LPI];
+                    if (COOP) encode_levels_pair<LPI>(M, LPI * c, sx, sy, sz, f);
+                    else encode_levels<LPI>(M, LPI * c, sx, sy, sz, f);
+                    if (s < n_s) {
+#pragma unroll
+                        for (int q = 0; q < LPI / 2; ++q) {
+                            uint4 v;
+                            v.x = *reinterpret_cast<uint32_t*>(&f[4 * q + 0]); v.y = *reinterpret_cast<uint32_t*>(&f[4 * q + 1]);
+                            v.z = *reinterpret_cast<uint32_t*>(&f[4 * q + 2]); v.w = *reinterpret_cast<uint32_t*>(&f[4 * q + 3]);
+                            *reinterpret_cast<uint4*>(rowA32 + s * T2_TILE + (c * (LPI / 2) + q) * 128) = v;
+                        }
                     }
                 }
             }
@@ -262,17 +286,11 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc2(const __grid_consta
             for (int s = 0; s < 2; ++s) {
                 if (alive && s < n_s) {
                     ++my_samples;                  // composited samples only (a dropped sample 1 is not counted)
-                    const float ux = M.aabb_min[0] + wp[s][0] * M.aabb_diag[0];
-                    const float uy = M.aabb_min[1] + wp[s][1] * M.aabb_diag[1];
-                    const float uz = M.aabb_min[2] + wp[s][2] * M.aabb_diag[2];
                     const float T = 1.f - R.ca;
-                    const float dtu = unwarp_dt(wdt[s]);
-                    const float alpha = 1.f - __expf(-__expf(s == 0 ? sigma0 : sigma1) * dtu);
+                    const float alpha = 1.f - __expf(-__expf(s == 0 ? sigma0 : sigma1) * (s == 0 ? dtu0 : dtu1));
                     const float weight = alpha * T;
                     const float rr = logistic_d(raw[s][0]), gg = logistic_d(raw[s][1]), bb_ = logistic_d(raw[s][2]);
-                    float dep = 0.f;
-                    dep += R.fwx * (ux - R.g.ox); dep += R.fwy * (uy - R.g.oy); dep += R.fwz * (uz - R.g.oz);
-                    dep *= M.depth_scale;
+                    const float dep = s == 0 ? dep0 : dep1;
                     R.cr += rr * weight; R.cg += gg * weight; R.cb += bb_ * weight; R.cd += dep * weight; R.ca += weight;
                     if (R.ca > (1.0f - M.min_transmittance)) {
                         R.cr /= R.ca; R.cg /= R.ca; R.cb /= R.ca; R.cd /= R.ca; R.ca /= R.ca;

@@ -236,6 +236,11 @@ extern "C" int d2r_model_load(const void* params_f16_host, size_t n_params, cons
     d.w_c1 = p; p += 64 * 64;
     d.w_c2 = p; p += 16 * 64;
     d.grid = p;
+    for (int l = 0; l < MAX_LEVELS; ++l) {
+        const bool used = l < cfg->n_levels;
+        d.level_table[l] = reinterpret_cast<const uint2*>(d.grid) + (used ? offsets[l] : 0);
+        d.level_size[l] = used ? offsets[l + 1] - offsets[l] : 1u;
+    }
     d.bitfield = m->bitfield_dev;
     bool ident = true;
     for (int i = 0; i < 3; ++i) {

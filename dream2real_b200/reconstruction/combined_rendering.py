@@ -54,6 +54,7 @@ class renderer:
         self.out_render_path = os.path.join(self.root, "cb_render")
         os.makedirs(self.out_render_path, exist_ok=True)
         self.last_n_samples = 0
+        self.count_samples = False    # True: read the network-sample count back after every launch (one host sync each)
 
     # ---- background -----------------------------------------------------------------------------
     def render_background(self, cam_matrix, view_idx, depth_gt=None, movable_mask=None):
@@ -110,8 +111,9 @@ class renderer:
             out = torch.empty((len(valid_poses), H, W, 3), dtype=torch.uint8, device=bg_image.device)
             for s in range(0, len(valid_poses), self.max_candidates_per_launch):
                 e = min(s + self.max_candidates_per_launch, len(valid_poses))
-                fg.render_composite_batch(cams[s:e, :3, :], W, H, bg_image, bg_depth, out_u8=out[s:e], count_samples=True)
-                self.last_n_samples += fg.last_n_samples
+                fg.render_composite_batch(cams[s:e, :3, :], W, H, bg_image, bg_depth, out_u8=out[s:e], count_samples=self.count_samples)
+                if self.count_samples:
+                    self.last_n_samples += fg.last_n_samples
             outs.append(out)
         renders = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         if save and len(render_cam_pose_idx) == 1:
