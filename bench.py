@@ -234,6 +234,14 @@ def run_ours(args):
     alg_bytes = int(ns.value) * 512 + rays * 23
     march_s = mm.value / 1e3
     achieved = alg_bytes / march_s / 1e9 if march_s > 0 else 0.0
+    # DRAM traffic of one march launch from the committed ncu --set full capture of the same launch shape (profiles/)
+    traffic = None
+    try:
+        summ = json.load(open(os.path.join(ROOT, "profiles", "march_ncu_summary.json")))
+        if summ.get("candidates_per_launch") == args.chunk and summ.get("resolution") == res and args.scene == summ.get("scene"):
+            traffic = summ["dram_bytes_per_launch"]
+    except Exception:
+        pass
     total = K * world
     value = total * args.steps / (ms / 1e3)
     out = {
@@ -250,7 +258,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(K * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_march (fused ray-march + composite)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "launches": int(nl.value),
+                     "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes / max(1, nl.value), "peak_source": peak_src, "launches": int(nl.value),
                      "avg_launch_ms": mm.value / max(1, nl.value), "share_of_step": mm.value / ms,
                      "note": "algorithmic bytes; both hash tables (~50 MB) are L2-resident so DRAM traffic is far lower (DESIGN.md section 5)"},
     }

@@ -11,6 +11,11 @@
 
 #include <vector>
 
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
 #include "d2r_common.cuh"
 #include "d2r_gemm_api.h"
 
@@ -210,6 +215,143 @@ __global__ void __launch_bounds__(128) k_attention(const __half* __restrict__ qk
     }
 }
 
+// Persistent, double-buffered version of k_attention: a CTA walks work items (image, head, 64-query block) and, inside
+// an item, the key blocks; while it computes one {Q, K, V} stage the next one is already in flight through cp.async
+// (no registers held), so the global-load latency that dominated the one-item-per-CTA kernel at T = 50 is hidden.
+// Arithmetic (mma.sync tiles, online softmax order) is identical to k_attention.
+constexpr int ATT_STAGE_HALVES = 3 * 64 * ATT_LD;                  // Q, K, V tiles of one stage
+constexpr int ATT2_SMEM = 2 * ATT_STAGE_HALVES * (int)sizeof(__half);
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 16 : 0;                                  // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(128, 3) k_attention2(const __half* __restrict__ qkv, int T, int d, int heads, int B, __half* __restrict__ out) {
+    extern __shared__ __align__(16) __half att_smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int qblocks = (T + ATT_BQ - 1) / ATT_BQ, kblocks = (T + ATT_BK - 1) / ATT_BK;
+    const long n_items = (long)B * heads * qblocks;
+    const long n_steps_total = n_items * kblocks;        // step = (item, key block), items strided over the grid
+    // steps of this CTA: items blockIdx.x, blockIdx.x + gridDim.x, ...; each with kblocks steps
+    const long my_items = n_items > blockIdx.x ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long my_steps = my_items * kblocks;
+    (void)n_steps_total;
+
+    auto issue = [&](long step) {                        // cp.async the tiles of local step `step` into stage step & 1
+        const long item = blockIdx.x + (step / kblocks) * (long)gridDim.x;
+        const int kb = (int)(step % kblocks);
+        const int qb = (int)(item % qblocks), head = (int)((item / qblocks) % heads), img = (int)(item / ((long)qblocks * heads));
+        const __half* base = qkv + (size_t)img * T * 3 * d + head * ATT_HD;
+        __half* st = att_smem + (step & 1) * ATT_STAGE_HALVES;
+        if (kb == 0) {
+            for (int i = tid; i < ATT_BQ * (ATT_HD / 8); i += 128) {
+                const int r = i / (ATT_HD / 8), c8 = i % (ATT_HD / 8);
+                const bool ok = qb * ATT_BQ + r < T;
+                cp_async_16(st + r * ATT_LD + c8 * 8, base + (size_t)(ok ? qb * ATT_BQ + r : 0) * 3 * d + c8 * 8, ok);
+            }
+        }
+        for (int i = tid; i < ATT_BK * (ATT_HD / 8); i += 128) {
+            const int r = i / (ATT_HD / 8), c8 = i % (ATT_HD / 8);
+            const bool ok = kb * ATT_BK + r < T;
+            const __half* row = base + (size_t)(ok ? kb * ATT_BK + r : 0) * 3 * d + c8 * 8;
+            cp_async_16(st + (64 + r) * ATT_LD + c8 * 8, row + d, ok);
+            cp_async_16(st + (128 + r) * ATT_LD + c8 * 8, row + 2 * d, ok);
+        }
+        cp_async_commit();
+    };
+
+    if (my_steps > 0) issue(0);
+    uint32_t qf[4][4];
+    float o[8][4];
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    for (long step = 0; step < my_steps; ++step) {
+        if (step + 1 < my_steps) { issue(step + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        const long item = blockIdx.x + (step / kblocks) * (long)gridDim.x;
+        const int kb = (int)(step % kblocks), k0 = kb * ATT_BK;
+        const int qb = (int)(item % qblocks), head = (int)((item / qblocks) % heads), img = (int)(item / ((long)qblocks * heads));
+        const int q0 = qb * ATT_BQ;
+        const __half* Qs = att_smem + (step & 1) * ATT_STAGE_HALVES;
+        const __half* Ks = Qs + 64 * ATT_LD;
+        const __half* Vs = Qs + 128 * ATT_LD;
+        if (kb == 0) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) ldmatrix_x4(qf[kk], Qs + (warp * 16 + (lane & 15)) * ATT_LD + kk * 16 + (lane >> 4) * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+            m0 = -INFINITY; m1 = -INFINITY; l0 = 0.f; l1 = 0.f;
+        }
+        float s[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                uint32_t bfr[4];
+                ldmatrix_x4(bfr, Ks + (jp * 16 + (lane & 7) + ((lane >> 4) << 3)) * ATT_LD + kk * 16 + ((lane >> 3) & 1) * 8);
+                mma_16816(s[2 * jp], qf[kk], bfr[0], bfr[1]);
+                mma_16816(s[2 * jp + 1], qf[kk], bfr[2], bfr[3]);
+            }
+        }
+        float mx0 = m0, mx1 = m1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int key = k0 + j * 8 + 2 * t4;
+            if (key >= T) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+            if (key + 1 >= T) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float c0 = expf(m0 - mx0), c1 = expf(m1 - mx1);
+        m0 = mx0; m1 = mx1;
+        float rs0 = 0.f, rs1 = 0.f;
+        uint32_t pf[8][2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float p0 = expf(s[j][0] - mx0), p1 = expf(s[j][1] - mx0), p2 = expf(s[j][2] - mx1), p3 = expf(s[j][3] - mx1);
+            rs0 += p0 + p1; rs1 += p2 + p3;
+            __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+            pf[j][0] = *reinterpret_cast<uint32_t*>(&h01);
+            pf[j][1] = *reinterpret_cast<uint32_t*>(&h23);
+            o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1;
+        }
+        l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t af[4] = {pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1]};
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                uint32_t bfr[4];
+                ldmatrix_x4_trans(bfr, Vs + (kk * 16 + (lane & 15)) * ATT_LD + jp * 16 + (lane >> 4) * 8);
+                mma_16816(o[2 * jp], af, bfr[0], bfr[1]);
+                mma_16816(o[2 * jp + 1], af, bfr[2], bfr[3]);
+            }
+        }
+        if (kb == kblocks - 1) {
+            float t0 = l0, t1 = l1;
+            t0 += __shfl_xor_sync(0xffffffffu, t0, 1); t0 += __shfl_xor_sync(0xffffffffu, t0, 2);
+            t1 += __shfl_xor_sync(0xffffffffu, t1, 1); t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+            const float i0 = 1.0f / t0, i1 = 1.0f / t1;
+            const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = head * ATT_HD + j * 8 + 2 * t4;
+                if (r0 < T) *reinterpret_cast<__half2*>(out + ((size_t)img * T + r0) * d + col) = __floats2half2_rn(o[j][0] * i0, o[j][1] * i0);
+                if (r1 < T) *reinterpret_cast<__half2*>(out + ((size_t)img * T + r1) * d + col) = __floats2half2_rn(o[j][2] * i1, o[j][3] * i1);
+            }
+        }
+        __syncthreads();      // every warp is done with this stage before the next iteration's prefetch overwrites it
+    }
+}
+
 __global__ void k_l2norm(const float* __restrict__ in, int rows, int D, float* __restrict__ out) {
     const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x % 32;
     if (row >= rows) return;
@@ -335,8 +477,23 @@ extern "C" int d2r_clip_load(const d2r_clip_cfg* cfg, const float* const* W, int
 }
 
 static int launch_attention(const d2r_clip* c, int B, cudaStream_t stream) {
-    dim3 grid((c->T + ATT_BQ - 1) / ATT_BQ, c->cfg.heads, B);
-    k_attention<<<grid, 128, 0, stream>>>(c->qkv, c->T, c->cfg.hidden, c->o);
+    static const bool old_kernel = []() { const char* e = getenv("D2R_ATT"); return e && strcmp(e, "old") == 0; }();
+    if (old_kernel) {
+        dim3 grid((c->T + ATT_BQ - 1) / ATT_BQ, c->cfg.heads, B);
+        k_attention<<<grid, 128, 0, stream>>>(c->qkv, c->T, c->cfg.hidden, c->o);
+    } else {
+        static bool attr_done[16] = {false};
+        static int n_sm[16] = {0};
+        const int dev = c->device & 15;
+        if (!attr_done[dev]) {
+            D2R_CUDA(cudaFuncSetAttribute(k_attention2, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
+            D2R_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, c->device));
+            attr_done[dev] = true;
+        }
+        const long items = (long)B * c->cfg.heads * ((c->T + ATT_BQ - 1) / ATT_BQ);
+        const int grid = (int)std::min<long>(items, (long)n_sm[dev] * 3);      // 54 KB of shared memory and ~144 registers per thread: 3 CTAs per SM
+        k_attention2<<<grid, 128, ATT2_SMEM, stream>>>(c->qkv, c->T, c->cfg.hidden, c->cfg.heads, B, c->o);
+    }
     count_launch();
     return D2R_OK;
 }

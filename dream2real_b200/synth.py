@@ -39,10 +39,10 @@ SCENES = {
                             ((0.25, -0.02, 0.0), (0.31, 0.04, 0.09)), ((0.52, 0.18, 0.0), (0.60, 0.26, 0.05))], spheres=[]),
     "pool_triangle": dict(scene_type=0, fg_r=0.028, fg_pos=(0.60, 0.10, 0.028), boxes=[],
                           spheres=[((0.40 + 0.05 * (i % 5), -0.08 + 0.05 * (i // 5), 0.028), 0.028) for i in range(15)]),
-    "shelf": dict(scene_type=1, fg_r=0.035, fg_pos=(0.45, 0.30, 0.10),
+    "shelf": dict(scene_type=1, fg_r=0.035, fg_pos=(0.45, 0.30, 0.10), cam_shift=(0.0, 0.40, 0.15),
                   boxes=[((0.30, 0.36, 0.0), (0.75, 0.50, 0.03)), ((0.30, 0.36, 0.20), (0.75, 0.50, 0.23)),
                          ((0.30, 0.36, 0.40), (0.75, 0.50, 0.43)), ((0.30, 0.48, 0.0), (0.75, 0.50, 0.45))], spheres=[]),
-    "synthetic8": dict(scene_type=1, fg_r=0.04, fg_pos=(0.60, 0.20, 0.06),
+    "synthetic8": dict(scene_type=1, fg_r=0.04, fg_pos=(0.60, 0.20, 0.06), cam_shift=(0.0, 0.40, 0.15),
                        boxes=[((0.30 + 0.11 * i, 0.36, 0.0), (0.38 + 0.11 * i, 0.44, 0.06 + 0.03 * i)) for i in range(4)],
                        spheres=[((0.32 + 0.12 * i, 0.30, 0.05), 0.04) for i in range(4)]),
 }
@@ -150,6 +150,7 @@ def make_scene(name: str, out_dir: str, log2_hashmap_size: int = 19, seed: int =
     cams_nerf = []
     for v in range(n_views):
         m = NERF_CAM.copy()
+        m[:3, 3] += np.asarray(spec.get("cam_shift", (0.0, 0.0, 0.0)))   # shelf scenes: the camera faces the shelf (y ~ 0.42)
         m[1, 3] += 0.06 * v          # second view: small sideways baseline
         cams_nerf.append(m)
     fg_pos = np.asarray(spec["fg_pos"], np.float64)
