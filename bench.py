@@ -145,6 +145,8 @@ def run_ours(args):
     cams = T1 @ (np.linalg.inv(valid_poses_ngp) @ T1) @ (np.linalg.inv(T1) @ render_poses_ngp[0])
     cams_ngp = fg.cams_to_ngp(cams[:, :3, :])
     u8 = torch.empty((args.chunk, res, res, 3), dtype=torch.uint8, device=device)
+    rects = torch.empty((args.chunk, 4), dtype=torch.int32, device=device)
+    bg_u8 = torch.empty((res, res, 3), dtype=torch.uint8, device=device)
     scores = torch.empty(K, dtype=torch.float32, device=device)
     gathered = torch.empty(K * world, dtype=torch.float32, device=device) if world > 1 else None
 
@@ -153,8 +155,9 @@ def run_ours(args):
     def step_resident():
         for s in range(0, K, args.chunk):
             e = min(s + args.chunk, K)
-            fg.render_composite_batch(cams_ngp[s:e], res, res, bg_image, bg_depth, out_u8=u8[: e - s], ngp_convention=True)
-            patches, _ = cv.preprocess(u8[: e - s], rot90=True)
+            fg.render_composite_batch(cams_ngp[s:e], res, res, bg_image, bg_depth, out_u8=u8[: e - s], ngp_convention=True,
+                                      rects_out=rects[: e - s], bg_u8_out=bg_u8)
+            patches, _ = cv.preprocess(u8[: e - s], rot90=True, bg_u8=bg_u8, rects=rects[: e - s])
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
             emb = cv.encode_patches(patches, e - s)
@@ -174,7 +177,7 @@ def run_ours(args):
         renderer.render (one call: background once, all candidates) -> score_renders -> scores back on the host."""
         vp = pinned_poses.numpy()
         out = rnd.render(vp, render_poses_ngp, [0], tm.depths[:1], tm.movable_masks, save=False, return_tensor=True)
-        scores.copy_(score_renders(out, cv, txt, n_goal=1))
+        scores.copy_(score_renders(out, cv, txt, n_goal=1, bg_u8=rnd.last_bg_u8, rects=rnd.last_rects))
         del out
         if world > 1:
             dist.all_gather_into_tensor(gathered, scores)

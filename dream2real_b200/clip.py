@@ -95,11 +95,21 @@ class ClipVision:
         self._patches = torch.empty((self.max_batch * self.n_patches, self.kp), dtype=torch.float16,
                                     device=torch.device("cuda", self.device))
 
-    def preprocess(self, images_u8, rot90: bool = True, want_pixels: bool = False):
-        """uint8 CUDA [K,H,W,3] -> (patch-major fp16 [K*np, kp], optional float32 pixel_values [K,3,R,R])."""
+    def preprocess(self, images_u8, rot90: bool = True, want_pixels: bool = False, bg_u8=None, rects=None):
+        """uint8 CUDA [K,H,W,3] -> (patch-major fp16 [K*np, kp], optional float32 pixel_values [K,3,R,R]).
+        bg_u8 [H,W,3] + rects int32 [K,4] (from Testbed.render_composite_batch): frames equal bg_u8 outside their
+        rectangle, so only the affected part of every resize is recomputed (bit-identical result)."""
         import torch
         K, H, W, _ = images_u8.shape
         assert images_u8.is_cuda and images_u8.dtype == torch.uint8 and images_u8.is_contiguous() and K <= self.max_batch
+        if bg_u8 is not None and rects is not None and not want_pixels:
+            assert bg_u8.is_cuda and bg_u8.dtype == torch.uint8 and tuple(bg_u8.shape) == (H, W, 3) and bg_u8.is_contiguous()
+            assert rects.is_cuda and rects.dtype == torch.int32 and tuple(rects.shape) == (K, 4) and rects.is_contiguous()
+            with torch.cuda.device(images_u8.device):
+                N.check(N.lib().d2r_clip_preprocess_delta(images_u8.data_ptr(), K, H, W, 1 if rot90 else 0, self.image_size, self.patch,
+                                                          N.f4(OPENAI_CLIP_MEAN), N.f4(OPENAI_CLIP_STD), bg_u8.data_ptr(), rects.data_ptr(),
+                                                          self._patches.data_ptr(), N.stream_ptr()), "clip_preprocess_delta")
+            return self._patches[: K * self.n_patches], None
         pix = torch.empty((K, 3, self.image_size, self.image_size), dtype=torch.float32, device=images_u8.device) if want_pixels else None
         with torch.cuda.device(images_u8.device):
             N.check(N.lib().d2r_clip_preprocess(images_u8.data_ptr(), K, H, W, 1 if rot90 else 0, self.image_size, self.patch,
@@ -114,13 +124,13 @@ class ClipVision:
             N.check(N.lib().d2r_clip_encode(self._h, patches.data_ptr(), K, out.data_ptr(), N.stream_ptr()), "clip_encode")
         return out
 
-    def encode_images(self, images_u8, rot90: bool = True):
+    def encode_images(self, images_u8, rot90: bool = True, bg_u8=None, rects=None):
         """L2-normalised image embeddings [K, proj] for uint8 CUDA images, batched by max_batch."""
         import torch
         outs = []
         for s in range(0, images_u8.shape[0], self.max_batch):
             chunk = images_u8[s:s + self.max_batch]
-            patches, _ = self.preprocess(chunk, rot90)
+            patches, _ = self.preprocess(chunk, rot90, bg_u8=bg_u8, rects=None if rects is None else rects[s:s + self.max_batch])
             outs.append(self.encode_patches(patches, chunk.shape[0]))
         return torch.cat(outs, 0)
 

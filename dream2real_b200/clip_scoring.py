@@ -60,9 +60,11 @@ def gather_scores(local_scores, n_total, world_size, rank, group=None):
     return out[:n_total]
 
 
-def score_renders(renders_u8, clip_vision, txt_embeds, n_goal=1):
-    """uint8 CUDA [K,H,W,3] (not yet rotated) -> ratio scores [K] (clip_scoring.py:145-203)."""
-    emb = clip_vision.encode_images(renders_u8, rot90=True)
+def score_renders(renders_u8, clip_vision, txt_embeds, n_goal=1, bg_u8=None, rects=None):
+    """uint8 CUDA [K,H,W,3] (not yet rotated) -> ratio scores [K] (clip_scoring.py:145-203).  bg_u8 / rects: what
+    renderer.render recorded about its frames (renderer.last_bg_u8 / last_rects), lets preprocessing skip the pixels
+    every frame shares with the background."""
+    emb = clip_vision.encode_images(renders_u8, rot90=True, bg_u8=bg_u8, rects=rects)
     return clip_vision.score(emb, txt_embeds, n_goal=n_goal)
 
 
@@ -97,6 +99,7 @@ def optimise_pose_grid(renderer,
     rank = torch.distributed.get_rank() if dist_on else 0
 
     renders = None
+    frame_bg, frame_rects = None, None
     if use_cache_renders:
         import cv2
         print('Using cached renders')
@@ -132,6 +135,7 @@ def optimise_pose_grid(renderer,
         if hi > lo:
             renders = renderer.render(valid_poses_ngp[lo:hi], render_poses_ngp, render_cam_pose_idx, depths_gt,
                                       task_model.movable_masks, save=save_renders and world == 1, return_tensor=True)
+            frame_bg, frame_rects = getattr(renderer, "last_bg_u8", None), getattr(renderer, "last_rects", None)
 
     task_model.free_visual_models()
 
@@ -160,7 +164,7 @@ def optimise_pose_grid(renderer,
     with torch.no_grad():
         if renders is not None and renders.shape[0] > 0:
             vision = _vision_for(clip_model, device.index, clip_batch_size)
-            local = score_renders(renders, vision, txt, n_goal=n_goal)
+            local = score_renders(renders, vision, txt, n_goal=n_goal, bg_u8=frame_bg, rects=frame_rects)
         else:
             local = torch.zeros(0, dtype=torch.float32, device=device)
         logits = gather_scores(local, valid_idxs.shape[0], world, rank) if world > 1 else local

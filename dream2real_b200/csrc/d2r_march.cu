@@ -475,7 +475,7 @@ static int ensure_scratch(int device, int K, int W, int H) {
 
 int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_host, int K, const float bg[4],
                  float* rgba_out, float* depth_out, const float* bg_rgba, const float* bg_depth, uint8_t* u8_out,
-                 unsigned long long* n_samples, cudaStream_t stream) {
+                 unsigned long long* n_samples, cudaStream_t stream, int* rects_out = nullptr, uint8_t* bg_u8_out = nullptr) {
     D2R_REQUIRE(m && v && cams_ngp_host && bg, "render: null argument");
     D2R_REQUIRE(K > 0, "render: K must be positive");
     D2R_REQUIRE(m->device == v->device && m->device < 16, "render: model and view live on different devices");
@@ -513,6 +513,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
                                                           M.occ_min[2], M.occ_max[0], M.occ_max[1], M.occ_max[2], 0, s.bbox, s.tiles);
     k_tile_prefix<<<1, 1024, 0, stream>>>(K, s.tiles, s.prefix, s.counter);
     count_launch(2);
+    if (rects_out) D2R_CUDA(cudaMemcpyAsync(rects_out, s.bbox, (size_t)K * sizeof(int4), cudaMemcpyDeviceToDevice, stream));
 
     // what a pixel no ray reaches looks like: accumulate 0, then the tonemap background blend
     const float w0 = bg[3];
@@ -521,6 +522,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     if (u8_out) {
         k_bg_u8<<<(W * H + 255) / 256, 256, 0, stream>>>(W * H, empty, (const float4*)bg_rgba, bg_depth, s.bg_u8);
         count_launch();
+        if (bg_u8_out) D2R_CUDA(cudaMemcpyAsync(bg_u8_out, s.bg_u8, (size_t)W * H * 3, cudaMemcpyDeviceToDevice, stream));
     }
     {
         dim3 grid(K, std::min((W * H * 3 / 16 + 255) / 256 + 1, 32));
@@ -632,6 +634,15 @@ extern "C" int d2r_render(const d2r_model* m, const d2r_view* v, const float* ca
                           float* rgba_out_dev, float* depth_out_dev, unsigned long long* n_samples_out_dev, void* stream) {
     return d2r::launch_march(m, v, cams_ngp_host, K, background_rgba, rgba_out_dev, depth_out_dev, nullptr, nullptr, nullptr,
                              n_samples_out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int d2r_render_composite_ex(const d2r_model* fg, const d2r_view* v, const float* cams_ngp_host, int K,
+                                       const float fg_background_rgba[4], const float* bg_rgba_dev, const float* bg_depth_dev,
+                                       uint8_t* rgb_u8_out_dev, int* rects_out_dev, uint8_t* bg_u8_out_dev,
+                                       unsigned long long* n_samples_out_dev, void* stream) {
+    if (!rgb_u8_out_dev) { d2r::set_error("d2r_render_composite_ex: rgb_u8_out_dev is null"); return D2R_ERR_INVALID; }
+    return d2r::launch_march(fg, v, cams_ngp_host, K, fg_background_rgba, nullptr, nullptr, bg_rgba_dev, bg_depth_dev, rgb_u8_out_dev,
+                             n_samples_out_dev, (cudaStream_t)stream, rects_out_dev, bg_u8_out_dev);
 }
 
 extern "C" int d2r_render_composite(const d2r_model* fg, const d2r_view* v, const float* cams_ngp_host, int K,

@@ -207,6 +207,100 @@ __global__ void k_score(const float* __restrict__ img, const float* __restrict__
     }
 }
 
+// ---- delta preprocessing ---------------------------------------------------------------------------------------
+// Every candidate frame equals the composited background outside the candidate's screen rectangle, so its resized
+// image equals the resized background except where a filter window touches the rectangle.  The background goes
+// through the two passes once; per candidate only the affected outputs are recomputed -- with the same integer
+// arithmetic on the same source bytes, hence bit-identical to resizing the whole frame -- and written over a copy
+// of the background's patch rows.
+struct DeltaRange { int i0, i1, xx0, xx1, yy0, yy1; };   // inclusive; xx1 < xx0: nothing to do
+
+__global__ void k_delta_ranges(int K, int W, int rot90, int R, const int4* __restrict__ rects, const int* __restrict__ hb,
+                               const int* __restrict__ vb, DeltaRange* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int4 r = rects[k];                       // x0, y0, x1, y1 (inclusive) in frame coordinates
+    DeltaRange d;
+    d.i0 = 0; d.i1 = -1; d.xx0 = 0; d.xx1 = -1; d.yy0 = 0; d.yy1 = -1;
+    if (r.z >= r.x && r.w >= r.y) {
+        // rotated image rot[i][j] = src[j][W-1-i]: rows <- frame columns (reversed), columns <- frame rows
+        const int i0 = rot90 ? W - 1 - r.z : r.y, i1 = rot90 ? W - 1 - r.x : r.w;
+        const int j0 = rot90 ? r.y : r.x, j1 = rot90 ? r.w : r.z;
+        int a = R, b = -1;
+        for (int xx = 0; xx < R; ++xx) {
+            const int lo = hb[2 * xx], hi = lo + hb[2 * xx + 1] - 1;
+            if (hi >= j0 && lo <= j1) { a = min(a, xx); b = max(b, xx); }
+        }
+        int c = R, e = -1;
+        for (int yy = 0; yy < R; ++yy) {
+            const int lo = vb[2 * yy], hi = lo + vb[2 * yy + 1] - 1;
+            if (hi >= i0 && lo <= i1) { c = min(c, yy); e = max(e, yy); }
+        }
+        d.i0 = i0; d.i1 = i1; d.xx0 = a; d.xx1 = b; d.yy0 = c; d.yy1 = e;
+    }
+    out[k] = d;
+}
+
+__global__ void k_copy_patches(const uint4* __restrict__ bg, size_t n16, uint4* __restrict__ dst) {
+    uint4* o = dst + (size_t)blockIdx.y * n16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) o[i] = __ldg(bg + i);
+}
+
+__global__ void k_resize_h_delta(const uint8_t* __restrict__ src, int H, int W, int rot90, int Hr, int R, int ksize,
+                                 const int* __restrict__ bounds, const int* __restrict__ kk, const DeltaRange* __restrict__ ranges,
+                                 uint8_t* __restrict__ tmp) {
+    const int k = blockIdx.z;
+    const DeltaRange d = ranges[k];
+    const uint8_t* img = src + (size_t)k * H * W * 3;
+    for (int xx = d.xx0 + blockIdx.y; xx <= d.xx1; xx += gridDim.y) {
+        const int xmin = bounds[xx * 2], xmax = bounds[xx * 2 + 1];
+        const int* kr = kk + (size_t)xx * ksize;
+        for (int i = d.i0 + blockIdx.x * blockDim.x + threadIdx.x; i <= d.i1; i += gridDim.x * blockDim.x) {
+            int s0 = 1 << (PRECISION_BITS - 1), s1 = s0, s2 = s0;
+            for (int x = 0; x < xmax; ++x) {
+                const int j = xmin + x;
+                const uint8_t* p = rot90 ? img + ((size_t)j * W + (W - 1 - i)) * 3 : img + ((size_t)i * W + j) * 3;
+                const int w = kr[x];
+                s0 += p[0] * w; s1 += p[1] * w; s2 += p[2] * w;
+            }
+            uint8_t* o = tmp + (((size_t)k * R + xx) * Hr + i) * 3;
+            o[0] = clip8(s0); o[1] = clip8(s1); o[2] = clip8(s2);
+        }
+    }
+}
+
+__global__ void k_resize_v_delta(const uint8_t* __restrict__ tmp, const uint8_t* __restrict__ bg_tmp, int Hr, int R, int ksize,
+                                 const int* __restrict__ bounds, const int* __restrict__ kk, const DeltaRange* __restrict__ ranges, int P,
+                                 int Kp, float m0, float m1, float m2, float i0_, float i1_, float i2_, __half* __restrict__ patches) {
+    const int k = blockIdx.z;
+    const DeltaRange d = ranges[k];
+    const float mean[3] = {m0, m1, m2}, stdv[3] = {i0_, i1_, i2_};
+    const int np_side = R / P;
+    for (int yy = d.yy0 + blockIdx.y; yy <= d.yy1; yy += gridDim.y) {
+        const int ymin = bounds[yy * 2], ymax = bounds[yy * 2 + 1];
+        const int* kr = kk + (size_t)yy * ksize;
+        for (int xx = d.xx0 + blockIdx.x * blockDim.x + threadIdx.x; xx <= d.xx1; xx += gridDim.x * blockDim.x) {
+            const uint8_t* own = tmp + (((size_t)k * R + xx) * Hr) * 3;
+            const uint8_t* bgr = bg_tmp + ((size_t)xx * Hr) * 3;
+            int s0 = 1 << (PRECISION_BITS - 1), s1 = s0, s2 = s0;
+            for (int y = 0; y < ymax; ++y) {
+                const int i = ymin + y;
+                const uint8_t* p = (i >= d.i0 && i <= d.i1 ? own : bgr) + (size_t)i * 3;
+                const int w = kr[y];
+                s0 += p[0] * w; s1 += p[1] * w; s2 += p[2] * w;
+            }
+            const uint8_t u[3] = {clip8(s0), clip8(s1), clip8(s2)};
+            const size_t prow = (size_t)k * np_side * np_side + (size_t)(yy / P) * np_side + xx / P;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = (float)((double)u[c] * (1.0 / 255.0));
+                const float nv = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
+                patches[prow * Kp + (size_t)c * P * P + (yy % P) * P + (xx % P)] = __float2half_rn(nv);
+            }
+        }
+    }
+}
+
 struct ResizePlan {
     int in_size = 0, out_size = 0, ksize = 0;
     int* bounds_dev = nullptr;
@@ -215,6 +309,9 @@ struct ResizePlan {
 static std::vector<ResizePlan> g_plans[16];
 static uint8_t* g_tmp[16] = {nullptr};
 static size_t g_tmp_cap[16] = {0};
+struct DeltaScratch { uint8_t* bg_tmp = nullptr; size_t bg_tmp_cap = 0; __half* bg_patches = nullptr; size_t bg_patches_cap = 0;
+                      DeltaRange* ranges = nullptr; int ranges_cap = 0; };
+static DeltaScratch g_delta[16];
 
 static int get_plan(int device, int in_size, int out_size, ResizePlan* out) {
     for (const ResizePlan& p : g_plans[device])
@@ -235,6 +332,9 @@ static int get_plan(int device, int in_size, int out_size, ResizePlan* out) {
 }  // namespace d2r
 
 using namespace d2r;
+
+static int run_full_resize(const uint8_t* rgb_u8_dev, int K, int H, int W, int rot90, int R, int P, const float mean[3], const float std_[3],
+                           const ResizePlan* ph, const ResizePlan* pv, uint8_t* tmp, __half* patches, float* pixels, cudaStream_t stream);
 
 extern "C" int d2r_clip_preprocess(const uint8_t* rgb_u8_dev, int K, int H, int W, int rot90, int R, int P, const float mean[3],
                                    const float std_[3], void* patches_out_dev, float* pixels_f32_out_dev, void* stream_) {
@@ -259,28 +359,89 @@ extern "C" int d2r_clip_preprocess(const uint8_t* rgb_u8_dev, int K, int H, int 
         D2R_CUDA(cudaMalloc(&g_tmp[device], tmp_bytes));
         g_tmp_cap[device] = tmp_bytes;
     }
-    {
-        if (rot90 && W % 4 == 0 && ((uintptr_t)rgb_u8_dev % 4) == 0) {
-            dim3 grid((W / 4 + 127) / 128, R, K);
-            k_resize_h_rot4<<<grid, 128, 0, stream>>>(rgb_u8_dev, H, W, R, ph->ksize, ph->bounds_dev, ph->kk_dev, g_tmp[device]);
-        } else {
-            dim3 grid((Hr + 127) / 128, R, K);
-            k_resize_h<<<grid, 128, 0, stream>>>(rgb_u8_dev, H, W, rot90, Hr, Wr, R, ph->ksize, ph->bounds_dev, ph->kk_dev, g_tmp[device]);
-        }
+    rc = run_full_resize(rgb_u8_dev, K, H, W, rot90, R, P, mean, std_, ph, pv, g_tmp[device], (__half*)patches_out_dev, pixels_f32_out_dev, stream);
+    if (rc) return rc;
+    D2R_CUDA(cudaGetLastError());
+    return D2R_OK;
+}
+
+static int run_full_resize(const uint8_t* rgb_u8_dev, int K, int H, int W, int rot90, int R, int P, const float mean[3], const float std_[3],
+                           const ResizePlan* ph, const ResizePlan* pv, uint8_t* tmp, __half* patches, float* pixels, cudaStream_t stream) {
+    const int Hr = rot90 ? W : H, Wr = rot90 ? H : W;
+    if (rot90 && W % 4 == 0 && ((uintptr_t)rgb_u8_dev % 4) == 0) {
+        dim3 grid((W / 4 + 127) / 128, R, K);
+        k_resize_h_rot4<<<grid, 128, 0, stream>>>(rgb_u8_dev, H, W, R, ph->ksize, ph->bounds_dev, ph->kk_dev, tmp);
+    } else {
+        dim3 grid((Hr + 127) / 128, R, K);
+        k_resize_h<<<grid, 128, 0, stream>>>(rgb_u8_dev, H, W, rot90, Hr, Wr, R, ph->ksize, ph->bounds_dev, ph->kk_dev, tmp);
     }
     const int K0 = 3 * P * P, Kp = (K0 + 63) / 64 * 64;
-    {
-        dim3 grid((R + 127) / 128, R, K);
-        k_resize_v_norm<<<grid, 128, 0, stream>>>(g_tmp[device], Hr, R, pv->ksize, pv->bounds_dev, pv->kk_dev, P, Kp, mean[0], mean[1],
-                                                  mean[2], std_[0], std_[1], std_[2], (__half*)patches_out_dev, pixels_f32_out_dev);
-    }
+    dim3 grid((R + 127) / 128, R, K);
+    k_resize_v_norm<<<grid, 128, 0, stream>>>(tmp, Hr, R, pv->ksize, pv->bounds_dev, pv->kk_dev, P, Kp, mean[0], mean[1], mean[2], std_[0],
+                                              std_[1], std_[2], patches, pixels);
     count_launch(2);
-    if (patches_out_dev && Kp != K0) {
+    if (patches && Kp != K0) {
         const size_t rows = (size_t)K * (R / P) * (R / P);
         dim3 block(32, 8);
-        k_zero_pad_cols<<<(unsigned)((rows + 7) / 8), block, 0, stream>>>((__half*)patches_out_dev, rows, Kp, K0);
+        k_zero_pad_cols<<<(unsigned)((rows + 7) / 8), block, 0, stream>>>(patches, rows, Kp, K0);
         count_launch();
     }
+    return D2R_OK;
+}
+
+extern "C" int d2r_clip_preprocess_delta(const uint8_t* rgb_u8_dev, int K, int H, int W, int rot90, int R, int P, const float mean[3],
+                                         const float std_[3], const uint8_t* bg_u8_dev, const int* rects_dev, void* patches_out_dev,
+                                         void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D2R_REQUIRE(rgb_u8_dev && mean && std_ && bg_u8_dev && rects_dev && patches_out_dev, "d2r_clip_preprocess_delta: null argument");
+    D2R_REQUIRE(K > 0 && H > 0 && W > 0 && R > 0 && P > 0 && R % P == 0, "d2r_clip_preprocess_delta: bad sizes");
+    D2R_REQUIRE(H == W, "d2r_clip_preprocess_delta: only square renders are on this path");
+    D2R_REQUIRE(K <= 65535, "d2r_clip_preprocess_delta: K must be <= 65535 per call");
+    int device;
+    D2R_CUDA(cudaGetDevice(&device));
+    D2R_REQUIRE(device < 16, "d2r_clip_preprocess_delta: device index too large");
+    const int Hr = rot90 ? W : H, Wr = rot90 ? H : W;
+    ResizePlan ph, pv;
+    int rc = get_plan(device, Wr, R, &ph);
+    if (rc) return rc;
+    rc = get_plan(device, Hr, R, &pv);
+    if (rc) return rc;
+    const size_t tmp_bytes = (size_t)K * R * Hr * 3 + 16;
+    if (tmp_bytes > g_tmp_cap[device]) {
+        if (g_tmp[device]) D2R_CUDA(cudaFree(g_tmp[device]));
+        D2R_CUDA(cudaMalloc(&g_tmp[device], tmp_bytes));
+        g_tmp_cap[device] = tmp_bytes;
+    }
+    DeltaScratch& ds = g_delta[device];
+    const int K0 = 3 * P * P, Kp = (K0 + 63) / 64 * 64, np = (R / P) * (R / P);
+    const size_t bg_tmp_bytes = (size_t)R * Hr * 3 + 16, bg_patch_elems = (size_t)np * Kp;
+    if (bg_tmp_bytes > ds.bg_tmp_cap) {
+        if (ds.bg_tmp) D2R_CUDA(cudaFree(ds.bg_tmp));
+        D2R_CUDA(cudaMalloc(&ds.bg_tmp, bg_tmp_bytes));
+        ds.bg_tmp_cap = bg_tmp_bytes;
+    }
+    if (bg_patch_elems > ds.bg_patches_cap) {
+        if (ds.bg_patches) D2R_CUDA(cudaFree(ds.bg_patches));
+        D2R_CUDA(cudaMalloc(&ds.bg_patches, bg_patch_elems * sizeof(__half)));
+        ds.bg_patches_cap = bg_patch_elems;
+    }
+    if (K > ds.ranges_cap) {
+        if (ds.ranges) D2R_CUDA(cudaFree(ds.ranges));
+        D2R_CUDA(cudaMalloc(&ds.ranges, (size_t)K * sizeof(DeltaRange)));
+        ds.ranges_cap = K;
+    }
+    // 1. the background frame through both passes (one image)
+    rc = run_full_resize(bg_u8_dev, 1, H, W, rot90, R, P, mean, std_, &ph, &pv, ds.bg_tmp, ds.bg_patches, nullptr, stream);
+    if (rc) return rc;
+    // 2. per candidate: affected output ranges, background patch rows, then the affected outputs only
+    k_delta_ranges<<<(K + 127) / 128, 128, 0, stream>>>(K, W, rot90, R, (const int4*)rects_dev, ph.bounds_dev, pv.bounds_dev, ds.ranges);
+    const size_t n16 = bg_patch_elems * sizeof(__half) / 16;       // Kp is a multiple of 64 halves
+    k_copy_patches<<<dim3(8, K), 256, 0, stream>>>((const uint4*)ds.bg_patches, n16, (uint4*)patches_out_dev);
+    k_resize_h_delta<<<dim3(2, 64, K), 128, 0, stream>>>(rgb_u8_dev, H, W, rot90, Hr, R, ph.ksize, ph.bounds_dev, ph.kk_dev, ds.ranges,
+                                                         g_tmp[device]);
+    k_resize_v_delta<<<dim3(1, 64, K), 64, 0, stream>>>(g_tmp[device], ds.bg_tmp, Hr, R, pv.ksize, pv.bounds_dev, pv.kk_dev, ds.ranges, P, Kp,
+                                                        mean[0], mean[1], mean[2], std_[0], std_[1], std_[2], (__half*)patches_out_dev);
+    count_launch(4);
     D2R_CUDA(cudaGetLastError());
     return D2R_OK;
 }

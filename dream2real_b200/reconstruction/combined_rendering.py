@@ -54,6 +54,8 @@ class renderer:
         self.out_render_path = os.path.join(self.root, "cb_render")
         os.makedirs(self.out_render_path, exist_ok=True)
         self.last_n_samples = 0
+        self.last_rects = None        # int32 CUDA [K,4] / uint8 CUDA [H,W,3] of the last single-view render(): outside its
+        self.last_bg_u8 = None        # rectangle a frame equals the composited background (clip_scoring exploits it)
         self.count_samples = False    # True: read the network-sample count back after every launch (one host sync each)
 
     # ---- background -----------------------------------------------------------------------------
@@ -109,12 +111,16 @@ class renderer:
             # T_WC_2 = T_WO_1 . (T_WO_2^-1 . T_WO_1) . (T_WO_1^-1 . T_WC_1), same association as the reference
             cams = T_WO_1 @ (inv_T_WO_2 @ T_WO_1) @ (np.linalg.inv(T_WO_1) @ T_WC_1)
             out = torch.empty((len(valid_poses), H, W, 3), dtype=torch.uint8, device=bg_image.device)
+            rects = torch.empty((len(valid_poses), 4), dtype=torch.int32, device=bg_image.device)
+            bg_u8 = torch.empty((H, W, 3), dtype=torch.uint8, device=bg_image.device)
             for s in range(0, len(valid_poses), self.max_candidates_per_launch):
                 e = min(s + self.max_candidates_per_launch, len(valid_poses))
-                fg.render_composite_batch(cams[s:e, :3, :], W, H, bg_image, bg_depth, out_u8=out[s:e], count_samples=self.count_samples)
+                fg.render_composite_batch(cams[s:e, :3, :], W, H, bg_image, bg_depth, out_u8=out[s:e], count_samples=self.count_samples,
+                                          rects_out=rects[s:e], bg_u8_out=bg_u8 if s == 0 else None)
                 if self.count_samples:
                     self.last_n_samples += fg.last_n_samples
             outs.append(out)
+            self.last_rects, self.last_bg_u8 = (rects, bg_u8) if len(render_cam_pose_idx) == 1 else (None, None)
         renders = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         if save and len(render_cam_pose_idx) == 1:
             import cv2

