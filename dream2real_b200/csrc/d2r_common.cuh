@@ -60,7 +60,8 @@ struct ModelDev {
     const __half* w_c0;  // [64,32]
     const __half* w_c1;  // [64,64]
     const __half* w_c2;  // [16,64]
-    const uint8_t* bitfield;           // [8 * 128^3 / 8]
+    const uint8_t* bitfield;           // [8 * 128^3 / 8], Morton order inside a cascade (the reference's layout; exported)
+    const uint8_t* bitfield_lin;       // same bits, cell (x,y,z) at bit x + 128*y + 128^2*z: what the march reads (no Morton encode)
     float aabb_min[3], aabb_diag[3];
     float raabb_min[3], raabb_max[3];
     float r2l[9];
@@ -79,6 +80,7 @@ struct d2r_model {
     d2r::ModelDev dev;
     void* params_dev;     // fp16 blob
     uint8_t* bitfield_dev;
+    uint8_t* bitfield_lin_dev;
     size_t n_params;
     d2r_model_cfg cfg;
 };

@@ -91,24 +91,30 @@ __device__ __forceinline__ uint32_t expand_bits_d(uint32_t v) {
 __device__ __forceinline__ uint32_t morton3D_d(uint32_t x, uint32_t y, uint32_t z) {
     return expand_bits_d(x) | (expand_bits_d(y) << 1) | (expand_bits_d(z) << 2);
 }
+// 2^-mip / 128 * 2^-mip as exact powers of two (scalbnf(1.0f, -mip), scalbnf(128.0f, -mip) without the library call)
+__device__ __forceinline__ float pow2_neg(uint32_t mip) { return __int_as_float((int)((127u - mip) << 23)); }
+__device__ __forceinline__ float res_of_mip(uint32_t mip) { return __int_as_float((int)((134u - mip) << 23)); }
+// cascaded_grid_idx_at (nerf_device.cuh:430-447): same cell arithmetic; the index is x + 128*y + 128^2*z into the
+// linearised copy of the bitfield instead of the Morton code (the bit it selects is the same cell's)
 __device__ __forceinline__ uint32_t cascaded_grid_idx_at(float px, float py, float pz, uint32_t mip) {
-    float mip_scale = scalbnf(1.0f, -(int)mip);
+    float mip_scale = pow2_neg(mip);
     px -= 0.5f; py -= 0.5f; pz -= 0.5f;
     px *= mip_scale; py *= mip_scale; pz *= mip_scale;
     px += 0.5f; py += 0.5f; pz += 0.5f;
     int ix = (int)(px * 128.0f), iy = (int)(py * 128.0f), iz = (int)(pz * 128.0f);
-    if (ix < 0 || ix >= 128 || iy < 0 || iy >= 128 || iz < 0 || iz >= 128) return 0xFFFFFFFFu;
-    return morton3D_d(ix, iy, iz);
+    if ((uint32_t)(ix | iy | iz) >= 128u) return 0xFFFFFFFFu;      // any coordinate negative or >= 128
+    return (uint32_t)ix | ((uint32_t)iy << 7) | ((uint32_t)iz << 14);
 }
-__device__ __forceinline__ bool density_grid_occupied_at(float px, float py, float pz, const uint8_t* __restrict__ bits, uint32_t mip) {
+__device__ __forceinline__ bool density_grid_occupied_at(float px, float py, float pz, const uint8_t* __restrict__ bits_lin, uint32_t mip) {
     uint32_t idx = cascaded_grid_idx_at(px, py, pz, mip);
     if (idx == 0xFFFFFFFFu) return false;
-    return __ldg(bits + idx / 8 + (NERF_GRID_N_CELLS * mip) / 8) & (1 << (idx % 8));
+    return __ldg(bits_lin + idx / 8 + (NERF_GRID_N_CELLS * mip) / 8) & (1 << (idx % 8));
 }
 __device__ __forceinline__ uint32_t mip_from_pos(float px, float py, float pz) {
-    int exponent;
+    // frexpf(maxval, &exponent): exponent field - 126 for normal numbers, 0 for zero (denormals are flushed: -ftz)
     float maxval = fmaxf(fmaxf(fabsf(px - 0.5f), fabsf(py - 0.5f)), fabsf(pz - 0.5f));
-    frexpf(maxval, &exponent);
+    const int e = (int)((__float_as_uint(maxval) >> 23) & 0xffu);
+    const int exponent = e ? e - 126 : 0;
     return (uint32_t)min(max(exponent + 1, 0), 7);
 }
 __device__ __forceinline__ float distance_to_next_voxel(float px, float py, float pz, float dx, float dy, float dz,
@@ -122,7 +128,7 @@ __device__ __forceinline__ float distance_to_next_voxel(float px, float py, floa
 }
 __device__ __forceinline__ float advance_to_next_voxel(float t, const StepC& cone, float px, float py, float pz, float dx, float dy,
                                                        float dz, float ix, float iy, float iz, uint32_t mip) {
-    float res = scalbnf(128.0f, -(int)mip);
+    float res = res_of_mip(mip);
     float t_target = t + distance_to_next_voxel(px, py, pz, dx, dy, dz, ix, iy, iz, res);
     t = to_stepping_space(t, cone);
     t_target = to_stepping_space(t_target, cone);
@@ -154,8 +160,8 @@ __device__ __forceinline__ float skip_to_occupied(float t, const StepC& cone, co
         // leaves the render aabb, which yields MAX_DEPTH as well)
         if (t >= MAX_DEPTH() || t > r.t_exit || !raabb_contains(M, px, py, pz)) return MAX_DEPTH();
         uint32_t mip = min(max(mip_from_pos(px, py, pz), 0u), max_mip);
-        if (density_grid_occupied_at(px, py, pz, M.bitfield, mip)) return t;
-        while (mip < max_mip && !density_grid_occupied_at(px, py, pz, M.bitfield, mip + 1)) ++mip;
+        if (density_grid_occupied_at(px, py, pz, M.bitfield_lin, mip)) return t;
+        while (mip < max_mip && !density_grid_occupied_at(px, py, pz, M.bitfield_lin, mip + 1)) ++mip;
         t = advance_to_next_voxel(t, cone, px, py, pz, r.dx, r.dy, r.dz, r.ix, r.iy, r.iz, mip);
     }
 }

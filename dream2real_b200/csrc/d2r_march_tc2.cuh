@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc2(const __grid_consta
                 const float px = R.g.ox + t * R.g.dx, py = R.g.oy + t * R.g.dy, pz = R.g.oz + t * R.g.dz;
                 if (t >= MAX_DEPTH() || t > R.g.t_exit || !raabb_contains(M, px, py, pz)) { exits = true; break; }
                 uint32_t mip = min(max(mip_from_pos(px, py, pz), 0u), max_mip);
-                if (density_grid_occupied_at(px, py, pz, M.bitfield, mip)) {
+                if (density_grid_occupied_at(px, py, pz, M.bitfield_lin, mip)) {
                     const float dt = calc_dt(t, cone);
                     const float wx = (px - M.aabb_min[0]) / M.aabb_diag[0];
                     const float wy = (py - M.aabb_min[1]) / M.aabb_diag[1];
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc2(const __grid_consta
                     if (++n_s == 2) break;
                     continue;
                 }
-                while (mip < max_mip && !density_grid_occupied_at(px, py, pz, M.bitfield, mip + 1)) ++mip;
+                while (mip < max_mip && !density_grid_occupied_at(px, py, pz, M.bitfield_lin, mip + 1)) ++mip;
                 t = advance_to_next_voxel(t, cone, px, py, pz, R.g.dx, R.g.dy, R.g.dz, R.g.ix, R.g.iy, R.g.iz, mip);
             }
             R.t = t;

@@ -56,6 +56,28 @@ __global__ void k_grid_to_bitfield(uint32_t n_elements, uint32_t n_nonzero, cons
     bits[i] = b;
 }
 
+// Morton-ordered cascade bitfields -> x + 128*y + 128^2*z order (one thread per output byte = 8 cells along x)
+__global__ void k_bitfield_linearise(uint32_t n_bytes_total, const uint8_t* __restrict__ morton, uint8_t* __restrict__ lin) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bytes_total) return;
+    const uint32_t casc = i / (NERF_GRID_N_CELLS / 8), b = i % (NERF_GRID_N_CELLS / 8);
+    const uint32_t cell0 = b * 8, x0 = cell0 & 127u, y = (cell0 >> 7) & 127u, z = cell0 >> 14;
+    auto expand = [](uint32_t v) {
+        v = (v * 0x00010001u) & 0xFF0000FFu;
+        v = (v * 0x00000101u) & 0x0F00F00Fu;
+        v = (v * 0x00000011u) & 0xC30C30C3u;
+        v = (v * 0x00000005u) & 0x49249249u;
+        return v;
+    };
+    const uint8_t* src = morton + (size_t)casc * (NERF_GRID_N_CELLS / 8);
+    uint32_t out = 0;
+    for (uint32_t j = 0; j < 8; ++j) {
+        const uint32_t m = expand(x0 + j) | (expand(y) << 1) | (expand(z) << 2);
+        out |= (uint32_t)((src[m >> 3] >> (m & 7)) & 1u) << j;
+    }
+    lin[i] = (uint8_t)out;
+}
+
 __global__ void k_bitfield_max_pool(uint32_t n_elements, const uint8_t* __restrict__ prev, uint8_t* __restrict__ next) {
     const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
     if (i >= n_elements) return;
@@ -184,6 +206,7 @@ extern "C" int d2r_model_load(const void* params_f16_host, size_t n_params, cons
     D2R_CUDA(cudaMemcpy(m->params_dev, params_f16_host, n_params * sizeof(__half), cudaMemcpyHostToDevice));
     const size_t bf_bytes = (size_t)NERF_GRID_N_CELLS / 8 * NERF_CASCADES;
     D2R_CUDA(cudaMalloc(&m->bitfield_dev, bf_bytes));
+    D2R_CUDA(cudaMalloc(&m->bitfield_lin_dev, bf_bytes));
 
     // occupancy bitfield
     float* grid_dev = nullptr;
@@ -199,7 +222,8 @@ extern "C" int d2r_model_load(const void* params_f16_host, size_t n_params, cons
     for (uint32_t level = 1; level < NERF_CASCADES; ++level)
         k_bitfield_max_pool<<<(n / 64 + 255) / 256, 256>>>(n / 64, m->bitfield_dev + (size_t)(level - 1) * (n / 8),
                                                          m->bitfield_dev + (size_t)level * (n / 8));
-    count_launch(2 + NERF_CASCADES - 1);
+    k_bitfield_linearise<<<(unsigned)((bf_bytes + 255) / 256), 256>>>((uint32_t)bf_bytes, m->bitfield_dev, m->bitfield_lin_dev);
+    count_launch(3 + NERF_CASCADES - 1);
     D2R_CUDA(cudaGetLastError());
 
     // level geometry on device
@@ -242,6 +266,7 @@ extern "C" int d2r_model_load(const void* params_f16_host, size_t n_params, cons
         d.level_size[l] = used ? offsets[l + 1] - offsets[l] : 1u;
     }
     d.bitfield = m->bitfield_dev;
+    d.bitfield_lin = m->bitfield_lin_dev;
     bool ident = true;
     for (int i = 0; i < 3; ++i) {
         d.aabb_min[i] = cfg->aabb_min[i];
@@ -303,6 +328,7 @@ extern "C" void d2r_model_free(d2r_model* m) {
     cudaSetDevice(m->device);
     cudaFree(m->params_dev);
     cudaFree(m->bitfield_dev);
+    cudaFree(m->bitfield_lin_dev);
     delete m;
 }
 
