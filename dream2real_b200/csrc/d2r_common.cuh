@@ -71,6 +71,7 @@ struct ModelDev {
     float min_transmittance;
     float depth_scale;
     float occ_min[3], occ_max[3];      // tight box of occupied cells
+    float occ_ctr[3], occ_r2;          // bounding sphere of the occupied cells (centre = box centre), radius^2 (< 0: none)
 };
 
 }  // namespace d2r

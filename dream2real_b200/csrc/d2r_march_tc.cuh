@@ -104,6 +104,17 @@ __device__ __forceinline__ bool setup_ray(const ModelDev& M, const Mat3x4& C, fl
     if (oc.x > 1e37f || oc.y < 0.f) return false;
     t_box = oc.x;
     r.t_exit = oc.y;
+    // ... and rays that miss the bounding sphere of the occupied cells; the chord through box AND sphere bounds the walk
+    {
+        const float cx = r.ox - M.occ_ctr[0], cy = r.oy - M.occ_ctr[1], cz = r.oz - M.occ_ctr[2];
+        const float b = cx * r.dx + cy * r.dy + cz * r.dz;            // |d| = 1
+        const float disc = b * b - (cx * cx + cy * cy + cz * cz - M.occ_r2);
+        if (disc < 0.f) return false;
+        const float sq = sqrtf(disc);
+        if (-b + sq < 0.f) return false;
+        t_box = fmaxf(t_box, -b - sq);
+        r.t_exit = fminf(r.t_exit, -b + sq);
+    }
     return true;
 }
 

@@ -315,6 +315,32 @@ extern "C" int d2r_model_load(const void* params_f16_host, size_t n_params, cons
             d.occ_min[a] = lo[a] - pad;
             d.occ_max[a] = hi[a] + pad;
         }
+        // bounding sphere of the occupied cells around the box centre (second pass: farthest cell corner); blob-shaped
+        // objects leave the corners of their box empty, and a ray is done once it is past box AND sphere
+        double r2 = 0.0;
+        const double ctr[3] = {0.5 * ((double)lo[0] + hi[0]), 0.5 * ((double)lo[1] + hi[1]), 0.5 * ((double)lo[2] + hi[2])};
+        for (int c = 0; c <= cfg->max_cascade; ++c) {
+            const uint8_t* b = bits.data() + (size_t)c * (n / 8);
+            const double size = ldexp(1.0, c), cell = size / 128.0;
+            for (uint32_t byte = 0; byte < n / 8; ++byte) {
+                if (!b[byte]) continue;
+                for (int j = 0; j < 8; ++j) {
+                    if (!(b[byte] & (1u << j))) continue;
+                    const uint32_t idx = byte * 8 + j;
+                    const uint32_t xyz[3] = {morton3D_invert(idx), morton3D_invert(idx >> 1), morton3D_invert(idx >> 2)};
+                    double dd = 0.0;
+                    for (int a = 0; a < 3; ++a) {
+                        const double c0 = 0.5 - 0.5 * size + cell * xyz[a], c1 = c0 + cell;
+                        const double far = std::max(std::fabs(c0 - ctr[a]), std::fabs(c1 - ctr[a]));
+                        dd += far * far;
+                    }
+                    r2 = std::max(r2, dd);
+                }
+            }
+        }
+        const double rad = std::sqrt(r2) * (1.0 + 1e-3) + 1e-3;     // conservative, like the box pad
+        for (int a = 0; a < 3; ++a) d.occ_ctr[a] = (float)ctr[a];
+        d.occ_r2 = lo[0] <= hi[0] ? (float)(rad * rad) : -1.0f;     // nothing occupied: no sphere
     }
     cudaFree(grid_dev);
     cudaFree(mean_dev);
