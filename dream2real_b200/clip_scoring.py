@@ -87,9 +87,18 @@ def optimise_pose_grid(renderer,
                        text_inputs=None,
                        save_renders=True,
                        show_best=False,
-                       clip_batch_size=512):
+                       clip_batch_size=512,
+                       multi_view="mean"):
+    """Reference signature and return value (clip_scoring.py:71-235).  Keyword-only extras: clip_model / clip_processor /
+    text_inputs (inject a loaded CLIP instead of downloading one), save_renders, show_best, clip_batch_size, and
+    multi_view: with more than one entry in render_cam_pose_idx the reference indexes K*L renders as if they were K
+    (clip_scoring.py:205-206 -- it only ever runs with one view); here the L per-view scores of a pose are averaged
+    ("mean") or the best view is taken ("max")."""
     if use_vis_pcds:
         raise NotImplementedError("the point-cloud ablation renderer is not on the accelerated path")
+    if multi_view not in ("mean", "max"):
+        raise ValueError("multi_view must be 'mean' or 'max'")
+    n_views = 1 if use_cache_renders else len(render_cam_pose_idx)
     if sample_res is None:
         sample_res = [40, 40, 1, 1, 1, 1]
     device = torch.device("cuda", torch.cuda.current_device())
@@ -165,6 +174,9 @@ def optimise_pose_grid(renderer,
         if renders is not None and renders.shape[0] > 0:
             vision = _vision_for(clip_model, device.index, clip_batch_size)
             local = score_renders(renders, vision, txt, n_goal=n_goal, bg_u8=frame_bg, rects=frame_rects)
+            if n_views > 1:      # renders are view-major [L*K]: one score per pose = mean (or max) over its L views
+                local = local.view(n_views, -1)
+                local = local.mean(0) if multi_view == "mean" else local.max(0).values
         else:
             local = torch.zeros(0, dtype=torch.float32, device=device)
         logits = gather_scores(local, valid_idxs.shape[0], world, rank) if world > 1 else local
@@ -186,7 +198,7 @@ def optimise_pose_grid(renderer,
     j = int(render_idxs[best_pose_idx])
     if renders is not None and lo <= j < hi:
         from PIL import Image
-        best_render = np.rot90(renders[j - lo].cpu().numpy(), k=1, axes=(0, 1))
+        best_render = np.rot90(renders[j - lo].cpu().numpy(), k=1, axes=(0, 1))     # first view of the best pose
         best_render = Image.fromarray(np.ascontiguousarray(best_render))
         best_render.save(os.path.join(data_dir, 'best_render.png'))
         if show_best:

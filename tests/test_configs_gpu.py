@@ -165,3 +165,30 @@ def test_delta_preprocessing_is_bit_identical(tmp_path, res, rot90):
         if x1 >= x0 and y1 >= y0:
             m[y0:y1 + 1, x0:x1 + 1] = False
         assert torch.equal(frames[k][m], r.last_bg_u8[m])
+
+
+def test_multi_view_scoring_is_the_mean_over_views(tmp_path):
+    """render_cam_pose_idx with L > 1 -> one score per pose = mean over its L per-view scores."""
+    import torch
+    from dream2real_b200 import clip_scoring, synth
+    from dream2real_b200.reconstruction.combined_rendering import renderer
+    from test_e2e_gpu import _tiny_clip
+    d = str(tmp_path)
+    scene = synth.make_scene("shopping", d, log2_hashmap_size=12, seed=4)
+    tm = synth.SyntheticTaskModel(scene, "goal", ["norm"], torch.device("cuda"))
+    model = _tiny_clip(11)
+    ids = torch.randint(3, 900, (2, 6))
+    ids[:, -1] = 2
+    kw = dict(sample_res=[3, 3, 1, 1, 1, 1], phys_check=synth.all_valid_phys_check, scene_type=3, smoothing=False, clip_model=model,
+              text_inputs={"input_ids": ids}, save_renders=False)
+    r = renderer(d, tm, resolution=64)
+    r.fix_mask_index = True
+    per_view = []
+    for v in (0, 1):
+        _, _, s = clip_scoring.optimise_pose_grid(r, tm.depths[v:v + 1], [v], tm, d, **kw)
+        per_view.append(s)
+    _, _, both = clip_scoring.optimise_pose_grid(r, tm.depths[:2], [0, 1], tm, d, **kw)
+    assert both.shape == per_view[0].shape
+    assert torch.allclose(both, (per_view[0] + per_view[1]) / 2, rtol=1e-5, atol=1e-6)
+    _, _, mx = clip_scoring.optimise_pose_grid(r, tm.depths[:2], [0, 1], tm, d, multi_view="max", **kw)
+    assert torch.allclose(mx, torch.maximum(per_view[0], per_view[1]), rtol=1e-5, atol=1e-6)
