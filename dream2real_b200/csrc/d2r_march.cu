@@ -507,6 +507,8 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     static const bool use_tc = []() { const char* e = getenv("D2R_MARCH"); return !(e && strcmp(e, "simt") == 0); }();
     static const int ctas_per_sm = []() { const char* e = getenv("D2R_MARCH_CTAS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 4 ? v : 4; }();
     static const bool use_solo = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "solo") == 0; }();    // per-thread gathers (no lane pairing)
+    static const int abl = []() { const char* e = getenv("D2R_MARCH_ABL"); return e ? atoi(e) : 0; }();   // timing ablations, wrong-free results
+    static const bool use_solo4 = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "solo4") == 0; }();
     static const bool use_lpi4 = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "lpi4") == 0; }();    // 4 levels per gather batch
     static const bool use_tc1 = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "tc1") == 0; }();   // one sample per round
     k_candidate_bbox<<<(K + 127) / 128, 128, 0, stream>>>(K, W, H, s.cams, col_lo, col_hi, row_lo, row_hi, M.occ_min[0], M.occ_min[1],
@@ -544,6 +546,9 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
         D2R_CUDA(cudaFuncSetAttribute(k_march_tc2<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
         D2R_CUDA(cudaFuncSetAttribute(k_march_tc2<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
         D2R_CUDA(cudaFuncSetAttribute(k_march_tc2<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
+        D2R_CUDA(cudaFuncSetAttribute(k_march_tc2<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
+        D2R_CUDA(cudaFuncSetAttribute((k_march_tc2<2, true, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
+        D2R_CUDA(cudaFuncSetAttribute((k_march_tc2<2, true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
         attr_set[m->device] = true;
     }
     Prof& pf = g_prof[m->device];
@@ -581,6 +586,9 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
             if (evp) D2R_CUDA(cudaEventRecord(evp->first, stream));   // time the march kernel alone
             if (use_tc1) k_march_tc<<<s.n_sm * 4, TC_THREADS, TS_TOTAL, stream>>>(P);
             else if (use_lpi4) k_march_tc2<4, true><<<s.n_sm * ctas_per_sm, TC_THREADS, T2_TOTAL, stream>>>(P);
+            else if (abl == 1) k_march_tc2<2, true, 1><<<s.n_sm * ctas_per_sm, TC_THREADS, T2_TOTAL, stream>>>(P);
+            else if (abl == 2) k_march_tc2<2, true, 2><<<s.n_sm * ctas_per_sm, TC_THREADS, T2_TOTAL, stream>>>(P);
+            else if (use_solo4) k_march_tc2<4, false><<<s.n_sm * ctas_per_sm, TC_THREADS, T2_TOTAL, stream>>>(P);
             else if (use_solo) k_march_tc2<2, false><<<s.n_sm * ctas_per_sm, TC_THREADS, T2_TOTAL, stream>>>(P);
             else k_march_tc2<2, true><<<s.n_sm * ctas_per_sm, TC_THREADS, T2_TOTAL, stream>>>(P);
             if (evp) { D2R_CUDA(cudaEventRecord(evp->second, stream)); evp = nullptr; }

@@ -339,11 +339,13 @@ __device__ __forceinline__ void encode_levels(const ModelDev& M, int level0, flo
 // the x+1 corner -> ONE line for the pair), set 2 serves the odd lane's sample, and a shuffle hands each lane the other
 // corner of its own sample.  Same number of loads, half the lines per instruction; the blend (order, rounding) is unchanged.
 template <int NL>
-__device__ __forceinline__ void encode_levels_pair(const ModelDev& M, int level0, float x, float y, float z, __half2* f /* [2 * NL] */) {
+__device__ __forceinline__ void encode_levels_pair(const ModelDev& M, int level0, float x, float y, float z, const float (&pe)[3],
+                                                   const float (&po)[3], __half2* f /* [2 * NL] */) {
+    // pe / po: position of the even / odd lane's sample of this pair (shuffled once per sample by the caller; the integer
+    // cell of either sample is recomputed per level with the same pos_fract arithmetic its owner uses)
     const uint32_t FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t odd = (uint32_t)lane & 1u;
-    const int lane_e = lane & ~1, lane_o = lane | 1;
     uint32_t e1[NL][4], e2[NL][4];
     float pos[NL][3];
     const uint2* table[NL];
@@ -358,11 +360,9 @@ __device__ __forceinline__ void encode_levels_pair(const ModelDev& M, int level0
 #pragma unroll
         for (int d = 0; d < 3; ++d) {    // pos_fract
             pos[l][d] = fmaf(scale, in[d], 0.5f);
-            float tmp = floorf(pos[l][d]);
-            const uint32_t pg = (uint32_t)(int)tmp;
-            pos[l][d] -= tmp;
-            pa[d] = __shfl_sync(FULL, pg, lane_e);
-            pb[d] = __shfl_sync(FULL, pg, lane_o);
+            pos[l][d] -= floorf(pos[l][d]);
+            pa[d] = (uint32_t)(int)floorf(fmaf(scale, pe[d], 0.5f));
+            pb[d] = (uint32_t)(int)floorf(fmaf(scale, po[d], 0.5f));
         }
         // set 1: this lane's corner of the even lane's sample has x offset `odd`; set 2 (odd lane's sample): offset `1 - odd`,
         // so that in both sets the lane that OWNS the sample fetches the x corner and its partner the x+1 corner
@@ -393,6 +393,7 @@ __device__ __forceinline__ void encode_levels_pair(const ModelDev& M, int level0
             }
         }
     }
+    (void)FULL;
     uint2 r1[NL][4], r2v[NL][4];
 #pragma unroll
     for (int l = 0; l < NL; ++l) {

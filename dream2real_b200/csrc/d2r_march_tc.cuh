@@ -60,9 +60,11 @@ __device__ __forceinline__ void issue_layer(uint32_t a_addr, uint32_t b_addr, in
 }
 
 __device__ __forceinline__ uint32_t pack_relu_h2(uint32_t a, uint32_t b, bool relu) {
-    __half2 h = __floats2half2_rn(__uint_as_float(a), __uint_as_float(b));
-    if (relu) h = __hmax2(h, __float2half2_rn(0.f));     // round-then-ReLU == ReLU-then-round, one op for two values
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t d;
+    // round-then-ReLU == ReLU-then-round; cvt.rn.relu.f16x2.f32 does both in one instruction (upper half <- first source)
+    if (relu) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(b)), "f"(__uint_as_float(a)));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(b)), "f"(__uint_as_float(a)));
+    return d;
 }
 
 struct TcRay {

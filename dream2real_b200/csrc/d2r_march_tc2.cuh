@@ -29,7 +29,7 @@ constexpr int T2_TOTAL = T2_MISC + 256;
 
 // LPI = hash-grid levels gathered per loop iteration (8 loads each in flight together): 2 or 4
 // COOP = lane-pair cooperative gathers (encode_levels_pair)
-template <int LPI, bool COOP>
+template <int LPI, bool COOP, int ABL = 0>   // ABL: timing ablations (1: encode twice, 2: walk twice, 3: every MMA round trip twice)
 __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc2(const __grid_constant__ MarchParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const ModelDev& M = P.M;
@@ -125,7 +125,10 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc2(const __grid_consta
         bool exits = false;                        // the ray leaves the occupied region after its last prepared sample
         float wp0x = 0.f, wp0y = 0.f, wp0z = 0.f, wp1x = 0.f, wp1y = 0.f, wp1z = 0.f;
         float dep0 = 0.f, dep1 = 0.f, dtu0 = 0.f, dtu1 = 0.f;     // what compositing needs of a sample: depth and unwarped dt
+#pragma unroll 1
+        for (int rep = (ABL == 2 ? 0 : 1); rep < 2; ++rep)
         if (alive) {
+            if (ABL == 2) { asm volatile("" :: "r"(n_s), "f"(dep0), "f"(dep1), "f"(wp0x), "f"(wp1x)); n_s = 0; exits = false; }
             float t = R.t;
             const uint32_t max_mip = (uint32_t)M.max_cascade;
             while (true) {
@@ -155,6 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc2(const __grid_consta
                 while (mip < max_mip && !density_grid_occupied_at(px, py, pz, M.bitfield_lin, mip + 1)) ++mip;
                 t = advance_to_next_voxel(t, cone, px, py, pz, R.g.dx, R.g.dy, R.g.dz, R.g.ix, R.g.iy, R.g.iz, mip);
             }
+            if (ABL == 2 && rep == 0) { asm volatile("" :: "f"(t)); continue; }
             R.t = t;
             if (n_s == 0) {                         // nothing left to sample: the ray is finished as it stands
                 finish(R.cr, R.cg, R.cb, R.cd, R.ca, R.ei);
@@ -167,11 +171,28 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_march_tc2(const __grid_consta
         for (int s = 0; s < 2; ++s) {
             if (__any_sync(0xffffffffu, s < n_s)) {
                 const float sx = s ? wp1x : wp0x, sy = s ? wp1y : wp0y, sz = s ? wp1z : wp0z;
+                float pe[3], po[3];            // the pair's two sample positions (lanes 2j / 2j+1), for the cooperative gather
+                if (COOP || ABL == 1) {
+                    const int lane_e = (tid & 31) & ~1, lane_o = (tid & 31) | 1;
+                    pe[0] = __shfl_sync(0xffffffffu, sx, lane_e); pe[1] = __shfl_sync(0xffffffffu, sy, lane_e); pe[2] = __shfl_sync(0xffffffffu, sz, lane_e);
+                    po[0] = __shfl_sync(0xffffffffu, sx, lane_o); po[1] = __shfl_sync(0xffffffffu, sy, lane_o); po[2] = __shfl_sync(0xffffffffu, sz, lane_o);
+                }
 #pragma unroll 1
                 for (int c = 0; c < 8 / LPI; ++c) {
                     __half2 f[2 * LPI];
-                    if (COOP) encode_levels_pair<LPI>(M, LPI * c, sx, sy, sz, f);
+                    __half2 fd[2 * LPI];
+                    if (ABL == 1) {
+                        const float qe[3] = {pe[0] * 0.97f + 0.011f, pe[1] * 0.97f + 0.013f, pe[2] * 0.97f + 0.017f};
+                        const float qo[3] = {po[0] * 0.97f + 0.011f, po[1] * 0.97f + 0.013f, po[2] * 0.97f + 0.017f};
+                        encode_levels_pair<LPI>(M, LPI * c, sx * 0.97f + 0.011f, sy * 0.97f + 0.013f, sz * 0.97f + 0.017f, qe, qo, fd);
+                    }
+                    if (COOP) encode_levels_pair<LPI>(M, LPI * c, sx, sy, sz, pe, po, f);
                     else encode_levels<LPI>(M, LPI * c, sx, sy, sz, f);
+                    if (ABL == 1) {
+                        const __half2 z = __float2half2_rn(M.depth_scale * 0.0f);      // a zero the compiler cannot see
+#pragma unroll
+                        for (int q = 0; q < 2 * LPI; ++q) f[q] = __hfma2(fd[q], z, f[q]);
+                    }
                     if (s < n_s) {
 #pragma unroll
                         for (int q = 0; q < LPI / 2; ++q) {
