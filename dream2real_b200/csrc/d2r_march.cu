@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(CTA, 3) k_march(const __grid_constant__ MarchP
 }  // namespace d2r
 #include "d2r_march_tc.cuh"
 #include "d2r_march_tc2.cuh"
+#include "d2r_march_split.cuh"
 namespace d2r {
 
 // ---- per-candidate screen rectangle + tile prefix ---------------------------------------------------
@@ -444,7 +445,12 @@ struct Scratch {   // per-device scratch reused across calls (grown on demand)
     RayEntry* entries = nullptr; size_t cap_entries = 0; uint32_t* entry_counters = nullptr;
     float4* res_rgbd = nullptr; float* res_a = nullptr;
     int n_sm = 0;
+    // round-based split path (k_gather_round / k_mlp_round)
+    size_t cap_split = 0;
+    unsigned char* sp_feat = nullptr; float2* sp_aux = nullptr; uint4* sp_shb = nullptr; uint8_t* sp_nsb = nullptr;
+    float* sp_t = nullptr; uint32_t* sp_live[2] = {nullptr, nullptr}; uint32_t* sp_cnt = nullptr;
 };
+constexpr int SPLIT_MAX_ROUNDS = MARCH_ITER / 2 + 2;
 static Scratch g_scratch[16];
 
 static int ensure_scratch(int device, int K, int W, int H) {
@@ -507,6 +513,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     static const bool use_tc = []() { const char* e = getenv("D2R_MARCH"); return !(e && strcmp(e, "simt") == 0); }();
     static const int ctas_per_sm = []() { const char* e = getenv("D2R_MARCH_CTAS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 4 ? v : 4; }();
     static const bool use_solo = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "solo") == 0; }();    // per-thread gathers (no lane pairing)
+    static const bool use_split = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "split") == 0; }();   // round-based gather / MLP kernels
     static const int abl = []() { const char* e = getenv("D2R_MARCH_ABL"); return e ? atoi(e) : 0; }();   // timing ablations, wrong-free results
     static const bool use_solo4 = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "solo4") == 0; }();
     static const bool use_lpi4 = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "lpi4") == 0; }();    // 4 levels per gather batch
@@ -584,7 +591,45 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
             k_classify<<<total_tiles, CTA, 0, stream>>>(P);
             count_launch();
             if (evp) D2R_CUDA(cudaEventRecord(evp->first, stream));   // time the march kernel alone
-            if (use_tc1) k_march_tc<<<s.n_sm * 4, TC_THREADS, TS_TOTAL, stream>>>(P);
+            if (use_split) {
+                if (need > s.cap_split) {
+                    cudaFree(s.sp_feat); cudaFree(s.sp_aux); cudaFree(s.sp_shb); cudaFree(s.sp_nsb); cudaFree(s.sp_t);
+                    cudaFree(s.sp_live[0]); cudaFree(s.sp_live[1]);
+                    const size_t blocks = (need + 127) / 128;
+                    D2R_CUDA(cudaMalloc(&s.sp_feat, blocks * 2 * SPLIT_TILE_BYTES));
+                    D2R_CUDA(cudaMalloc(&s.sp_aux, blocks * 2 * 128 * sizeof(float2)));
+                    D2R_CUDA(cudaMalloc(&s.sp_shb, blocks * 128 * 2 * sizeof(uint4)));
+                    D2R_CUDA(cudaMalloc(&s.sp_nsb, blocks * 128));
+                    D2R_CUDA(cudaMalloc(&s.sp_t, need * sizeof(float)));
+                    D2R_CUDA(cudaMalloc(&s.sp_live[0], need * sizeof(uint32_t)));
+                    D2R_CUDA(cudaMalloc(&s.sp_live[1], need * sizeof(uint32_t)));
+                    s.cap_split = need;
+                }
+                if (!s.sp_cnt) D2R_CUDA(cudaMalloc(&s.sp_cnt, (SPLIT_MAX_ROUNDS + 2) * sizeof(uint32_t)));
+                D2R_CUDA(cudaMemsetAsync(s.sp_cnt, 0, (SPLIT_MAX_ROUNDS + 2) * sizeof(uint32_t), stream));
+                static bool split_attr[16] = {false};
+                if (!split_attr[m->device]) {
+                    D2R_CUDA(cudaFuncSetAttribute(k_mlp_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
+                    split_attr[m->device] = true;
+                }
+                SplitParams Q;
+                Q.feat = s.sp_feat; Q.aux = s.sp_aux; Q.shb = s.sp_shb; Q.nsb = s.sp_nsb; Q.t_cur = s.sp_t;
+                for (int r = 0; r < SPLIT_MAX_ROUNDS; ++r) {
+                    Q.round = r;
+                    Q.cnt_in = s.sp_cnt + r; Q.cnt_out = s.sp_cnt + r + 1;
+                    Q.live_in = s.sp_live[r & 1]; Q.live_out = s.sp_live[(r + 1) & 1];
+                    k_gather_round<<<s.n_sm * 6, 128, 0, stream>>>(P, Q);
+                    k_mlp_round<<<s.n_sm * 4, TC_THREADS, T2_TOTAL, stream>>>(P, Q);
+                    count_launch(2);
+                    if ((r & 7) == 7) {                 // every 8 rounds: is anything left?  (one 4-byte read-back)
+                        uint32_t left = 0;
+                        D2R_CUDA(cudaMemcpyAsync(&left, s.sp_cnt + r + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+                        D2R_CUDA(cudaStreamSynchronize(stream));
+                        if (!left) break;
+                    }
+                }
+            }
+            else if (use_tc1) k_march_tc<<<s.n_sm * 4, TC_THREADS, TS_TOTAL, stream>>>(P);
             else if (use_lpi4) k_march_tc2<4, true><<<s.n_sm * ctas_per_sm, TC_THREADS, T2_TOTAL, stream>>>(P);
             else if (abl == 1) k_march_tc2<2, true, 1><<<s.n_sm * ctas_per_sm, TC_THREADS, T2_TOTAL, stream>>>(P);
             else if (abl == 2) k_march_tc2<2, true, 2><<<s.n_sm * ctas_per_sm, TC_THREADS, T2_TOTAL, stream>>>(P);

@@ -1,0 +1,345 @@
+// Round-based split of the ray march: k_gather_round (walk + hash-grid gather, no barriers, no tensor-core state ->
+// few registers, many warps per SM) and k_mlp_round (the five MLP layers on tcgen05 + compositing), alternating until no
+// ray is left.  Included by d2r_march.cu after d2r_march_tc2.cuh (shares its helpers and shared-memory plan).
+//
+// Why: the fused kernel (k_march_tc2) runs at 16 warps per SM -- 128 registers per thread, all TMEM columns, 208 KB of
+// shared memory -- and every component's latency (walk, gather, five MMA round trips) is exposed in full: the kernel's time
+// does not depend on the table size (2^14 vs 2^19 entries: same time per sample), doubling the gather adds 55 %, doubling
+// the walk 17 % (profiles/).  The gather needs neither TMEM nor shared memory, so on its own it runs at 3x the occupancy.
+// Price: 64 B of fp16 features per sample go through HBM once (written in the UMMA canonical operand layout, so the MLP
+// kernel stages them with plain 16-byte copies), plus 24 B of per-ray accumulators per round.
+//
+// Per round r every live ray takes its next (up to) two samples -- the same walk, features and compositing arithmetic as
+// k_march_tc2, so the results are identical; a ray that finishes keeps its accumulators in res_rgbd / res_a (k_finish turns
+// them into pixels), a ray that continues is appended to the next round's live list.  A live ray of round r has taken
+// exactly 2 r samples, so the reference's step counter needs no storage.
+#pragma once
+
+namespace d2r {
+
+struct SplitParams {
+    int round;
+    const uint32_t* cnt_in;     // live rays of this round (round 0: *n_entries)
+    uint32_t* cnt_out;          // appended to by k_mlp_round
+    const uint32_t* live_in;    // entry ids (round 0: identity)
+    uint32_t* live_out;
+    unsigned char* feat;        // [block][2][8 KB]: sample tile = 128 rows x 32 fp16 in UMMA canonical K-major layout
+    float2* aux;                // [block][2][128]: (depth of the sample, unwarped dt)
+    uint4* shb;                 // [block][128][2]: 16 fp16 SH coefficients of the ray direction
+    uint8_t* nsb;               // [block*128]: samples prepared (0..2) | 16 if the ray leaves the occupied region after them
+    float* t_cur;               // [entries]: ray parameter after the samples taken so far
+};
+
+constexpr int SPLIT_TILE_BYTES = 128 * 32 * 2;
+
+__global__ void __launch_bounds__(128, 6) k_gather_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
+    const ModelDev& M = P.M;
+    const int tid = threadIdx.x;
+    const uint32_t n_live = Q.round == 0 ? *P.n_entries : *Q.cnt_in;
+    const StepC cone = make_stepc(M.cone);
+    const uint32_t max_mip = (uint32_t)M.max_cascade;
+    unsigned long long my_samples = 0;
+    for (uint32_t blk = blockIdx.x; (size_t)blk * 128 < n_live; blk += gridDim.x) {
+        const uint32_t i = blk * 128 + tid;
+        if (i >= n_live) continue;
+        const uint32_t e = Q.round == 0 ? i : Q.live_in[i];
+        const RayEntry en = P.entries[e];
+        const Mat3x4 C = P.cams[en.k];
+        RayGeom g;
+        float t0, t_box;
+        setup_ray(M, C, __ldg(P.dirs + en.idx), g, t0, t_box);      // same arithmetic as pass 1
+        g.t_exit = en.t_exit;
+        float t = Q.round == 0 ? en.t : Q.t_cur[e];
+        const float fwx = C.c[2][0], fwy = C.c[2][1], fwz = C.c[2][2];
+        {
+            float sh[16];
+            const float wx = (g.dx + 1.0f) * 0.5f, wy = (g.dy + 1.0f) * 0.5f, wz = (g.dz + 1.0f) * 0.5f;
+            sh_enc4(wx * 2.f - 1.f, wy * 2.f - 1.f, wz * 2.f - 1.f, sh);
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                __half2 h = __floats2half2_rn(sh[2 * j], sh[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            Q.shb[(size_t)i * 2] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            Q.shb[(size_t)i * 2 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        // the walk of k_march_tc2 (phase B), verbatim
+        int n_s = 0;
+        bool exits = false;
+        float wp0x = 0.f, wp0y = 0.f, wp0z = 0.f, wp1x = 0.f, wp1y = 0.f, wp1z = 0.f;
+        float dep0 = 0.f, dep1 = 0.f, dtu0 = 0.f, dtu1 = 0.f;
+        while (true) {
+            const float px = g.ox + t * g.dx, py = g.oy + t * g.dy, pz = g.oz + t * g.dz;
+            if (t >= MAX_DEPTH() || t > g.t_exit || !raabb_contains(M, px, py, pz)) { exits = true; break; }
+            uint32_t mip = min(max(mip_from_pos(px, py, pz), 0u), max_mip);
+            if (density_grid_occupied_at(px, py, pz, M.bitfield_lin, mip)) {
+                const float dt = calc_dt(t, cone);
+                const float wx = (px - M.aabb_min[0]) / M.aabb_diag[0];
+                const float wy = (py - M.aabb_min[1]) / M.aabb_diag[1];
+                const float wz = (pz - M.aabb_min[2]) / M.aabb_diag[2];
+                const float ux = M.aabb_min[0] + wx * M.aabb_diag[0];
+                const float uy = M.aabb_min[1] + wy * M.aabb_diag[1];
+                const float uz = M.aabb_min[2] + wz * M.aabb_diag[2];
+                float dep = 0.f;
+                dep += fwx * (ux - g.ox); dep += fwy * (uy - g.oy); dep += fwz * (uz - g.oz);
+                dep *= M.depth_scale;
+                const float dtu = unwarp_dt(warp_dt(dt));
+                if (n_s == 0) { wp0x = wx; wp0y = wy; wp0z = wz; dep0 = dep; dtu0 = dtu; }
+                else { wp1x = wx; wp1y = wy; wp1z = wz; dep1 = dep; dtu1 = dtu; }
+                t += dt;
+                if (++n_s == 2) break;
+                continue;
+            }
+            while (mip < max_mip && !density_grid_occupied_at(px, py, pz, M.bitfield_lin, mip + 1)) ++mip;
+            t = advance_to_next_voxel(t, cone, px, py, pz, g.dx, g.dy, g.dz, g.ix, g.iy, g.iz, mip);
+        }
+        Q.t_cur[e] = t;
+        Q.nsb[i] = (uint8_t)(n_s | (exits ? 16 : 0));
+        Q.aux[((size_t)blk * 2 + 0) * 128 + tid] = make_float2(dep0, dtu0);
+        Q.aux[((size_t)blk * 2 + 1) * 128 + tid] = make_float2(dep1, dtu1);
+        my_samples += (unsigned)n_s;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (s < n_s) {
+                const float sx = s ? wp1x : wp0x, sy = s ? wp1y : wp0y, sz = s ? wp1z : wp0z;
+                unsigned char* row = Q.feat + ((size_t)blk * 2 + s) * SPLIT_TILE_BYTES + umma_chunk_off(tid, 0, 32);
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    __half2 f[4];
+                    encode_levels<2>(M, 2 * c, sx, sy, sz, f);
+                    uint4 v;
+                    v.x = *reinterpret_cast<uint32_t*>(&f[0]); v.y = *reinterpret_cast<uint32_t*>(&f[1]);
+                    v.z = *reinterpret_cast<uint32_t*>(&f[2]); v.w = *reinterpret_cast<uint32_t*>(&f[3]);
+                    *reinterpret_cast<uint4*>(row + c * 128) = v;
+                }
+            }
+        }
+    }
+    (void)my_samples;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const ModelDev& M = P.M;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + T2_MISC);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T2_MISC + 8);
+
+    stage_weights(smem + T2_WD0, M.w_d0, 64, 32, tid);
+    stage_weights(smem + T2_WD1, M.w_d1, 16, 64, tid);
+    stage_weights(smem + T2_WC0, M.w_c0, 64, 32, tid);
+    stage_weights(smem + T2_WC1, M.w_c1, 64, 64, tid);
+    stage_weights(smem + T2_WC2, M.w_c2, 16, 64, tid);
+    if (tid == 0) { mbar_init(mbar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc<128>(tmem_slot);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t a32 = smem_u32(smem + T2_A32), a64 = smem_u32(smem + T2_A64);
+    const uint32_t wd0 = smem_u32(smem + T2_WD0), wd1 = smem_u32(smem + T2_WD1), wc0 = smem_u32(smem + T2_WC0),
+                   wc1 = smem_u32(smem + T2_WC1), wc2 = smem_u32(smem + T2_WC2);
+    unsigned char* rowA32 = smem + T2_A32 + umma_chunk_off(tid, 0, 32);
+    unsigned char* rowA64 = smem + T2_A64 + umma_chunk_off(tid, 0, 64);
+    uint32_t phase = 0;
+    const uint32_t n_live = Q.round == 0 ? *P.n_entries : *Q.cnt_in;
+    unsigned long long my_samples = 0, my_rays = 0;
+    auto issue2 = [&](uint32_t a_addr, uint32_t a_tile_bytes, uint32_t b_addr, int K, int N) {
+        const uint32_t idesc = umma_idesc_f16(128, N, 0);
+        const uint32_t sbo = (uint32_t)(K / 8) * 128;
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            for (int kk = 0; kk < K / 16; ++kk) {
+                const uint64_t da = umma_desc_noswz(a_addr + s * a_tile_bytes + kk * 256, 128, sbo);
+                const uint64_t db = umma_desc_noswz(b_addr + kk * 256, 128, sbo);
+                umma_f16_ss(tmem_base + s * 64, da, db, idesc, kk > 0);
+            }
+        }
+        tc_commit(mbar);
+    };
+
+    for (uint32_t blk = blockIdx.x; (size_t)blk * 128 < n_live; blk += gridDim.x) {
+        const uint32_t i = blk * 128 + tid;
+        const bool valid = i < n_live;
+        const uint32_t ns_raw = valid ? Q.nsb[i] : 0u;
+        const int n_s = (int)(ns_raw & 15u);
+        const bool exits = (ns_raw & 16u) != 0;
+        const uint32_t e = valid ? (Q.round == 0 ? i : Q.live_in[i]) : 0u;
+        // this slot's rows of the two sample tiles: already in operand layout, 4 x 16 bytes each
+        {
+            const unsigned char* src = Q.feat + (size_t)blk * 2 * SPLIT_TILE_BYTES + umma_chunk_off(tid, 0, 32);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (s < n_s) v = *reinterpret_cast<const uint4*>(src + s * SPLIT_TILE_BYTES + c * 128);
+                    *reinterpret_cast<uint4*>(rowA32 + s * T2_TILE + c * 128) = v;
+                }
+            }
+        }
+        float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, ca = 0.f;
+        if (valid && Q.round > 0) {
+            const float4 a = P.res_rgbd[e];
+            cr = a.x; cg = a.y; cb = a.z; cd = a.w; ca = P.res_a[e];
+        }
+        uint4 sh0 = make_uint4(0, 0, 0, 0), sh1 = sh0;
+        float2 ax0 = make_float2(0.f, 0.f), ax1 = ax0;
+        if (valid) {
+            sh0 = Q.shb[(size_t)i * 2]; sh1 = Q.shb[(size_t)i * 2 + 1];
+            ax0 = Q.aux[((size_t)blk * 2 + 0) * 128 + tid];
+            ax1 = Q.aux[((size_t)blk * 2 + 1) * 128 + tid];
+        }
+        if (valid && Q.round == 0) ++my_rays;
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        // ---- density layer 0: 32 -> 64, ReLU ----
+        if (tid == 0) { tc_fence_after(); issue2(a32, T2_TILE, wd0, 32, 64); }
+        mbar_wait(mbar, phase); phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            uint32_t r[64];
+            tmem_ld_32x32_x64(tmem_lane + s * 64, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint4 v;
+                v.x = pack_relu_h2(r[8 * c + 0], r[8 * c + 1], true); v.y = pack_relu_h2(r[8 * c + 2], r[8 * c + 3], true);
+                v.z = pack_relu_h2(r[8 * c + 4], r[8 * c + 5], true); v.w = pack_relu_h2(r[8 * c + 6], r[8 * c + 7], true);
+                *reinterpret_cast<uint4*>(rowA64 + s * T2_TILE + c * 128) = v;
+            }
+        }
+        fence_proxy_async(); tc_fence_before(); __syncthreads();
+        // ---- density layer 1: 64 -> 16 (row 0 = raw density); rgb input = [16 density-out | 16 SH] ----
+        if (tid == 0) { tc_fence_after(); issue2(a64, T2_TILE, wd1, 64, 16); }
+        mbar_wait(mbar, phase); phase ^= 1;
+        tc_fence_after();
+        float sigma0 = 0.f, sigma1 = 0.f;
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            uint32_t r[16];
+            tmem_ld_32x32_x16(tmem_lane + s * 64, r);
+            tmem_ld_wait();
+            const float sg = h2f_round(__uint_as_float(r[0]));
+            if (s == 0) sigma0 = sg; else sigma1 = sg;
+            uint4 v0, v1;
+            v0.x = pack_relu_h2(r[0], r[1], false); v0.y = pack_relu_h2(r[2], r[3], false);
+            v0.z = pack_relu_h2(r[4], r[5], false); v0.w = pack_relu_h2(r[6], r[7], false);
+            v1.x = pack_relu_h2(r[8], r[9], false); v1.y = pack_relu_h2(r[10], r[11], false);
+            v1.z = pack_relu_h2(r[12], r[13], false); v1.w = pack_relu_h2(r[14], r[15], false);
+            unsigned char* row = rowA32 + s * T2_TILE;
+            *reinterpret_cast<uint4*>(row + 0) = v0;
+            *reinterpret_cast<uint4*>(row + 128) = v1;
+            *reinterpret_cast<uint4*>(row + 256) = sh0;
+            *reinterpret_cast<uint4*>(row + 384) = sh1;
+        }
+        fence_proxy_async(); tc_fence_before(); __syncthreads();
+        // ---- rgb layer 0: 32 -> 64, ReLU ----
+        if (tid == 0) { tc_fence_after(); issue2(a32, T2_TILE, wc0, 32, 64); }
+        mbar_wait(mbar, phase); phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            uint32_t r[64];
+            tmem_ld_32x32_x64(tmem_lane + s * 64, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint4 v;
+                v.x = pack_relu_h2(r[8 * c + 0], r[8 * c + 1], true); v.y = pack_relu_h2(r[8 * c + 2], r[8 * c + 3], true);
+                v.z = pack_relu_h2(r[8 * c + 4], r[8 * c + 5], true); v.w = pack_relu_h2(r[8 * c + 6], r[8 * c + 7], true);
+                *reinterpret_cast<uint4*>(rowA64 + s * T2_TILE + c * 128) = v;
+            }
+        }
+        fence_proxy_async(); tc_fence_before(); __syncthreads();
+        // ---- rgb layer 1: 64 -> 64, ReLU ----
+        if (tid == 0) { tc_fence_after(); issue2(a64, T2_TILE, wc1, 64, 64); }
+        mbar_wait(mbar, phase); phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            uint32_t r[64];
+            tmem_ld_32x32_x64(tmem_lane + s * 64, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint4 v;
+                v.x = pack_relu_h2(r[8 * c + 0], r[8 * c + 1], true); v.y = pack_relu_h2(r[8 * c + 2], r[8 * c + 3], true);
+                v.z = pack_relu_h2(r[8 * c + 4], r[8 * c + 5], true); v.w = pack_relu_h2(r[8 * c + 6], r[8 * c + 7], true);
+                *reinterpret_cast<uint4*>(rowA64 + s * T2_TILE + c * 128) = v;
+            }
+        }
+        fence_proxy_async(); tc_fence_before(); __syncthreads();
+        // ---- rgb output layer: 64 -> 16 (3 used) ----
+        if (tid == 0) { tc_fence_after(); issue2(a64, T2_TILE, wc2, 64, 16); }
+        mbar_wait(mbar, phase); phase ^= 1;
+        tc_fence_after();
+        float raw[2][3];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            uint32_t r[16];
+            tmem_ld_32x32_x16(tmem_lane + s * 64, r);
+            tmem_ld_wait();
+            raw[s][0] = h2f_round(__uint_as_float(r[0])); raw[s][1] = h2f_round(__uint_as_float(r[1])); raw[s][2] = h2f_round(__uint_as_float(r[2]));
+        }
+        // ---- composite_kernel_nerf (testbed_nerf.cu:511-667), sample 0 then sample 1; same arithmetic as k_march_tc2 ----
+        bool alive = valid;
+        bool finished = false;
+        if (alive) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (alive && s < n_s) {
+                    ++my_samples;
+                    const float T = 1.f - ca;
+                    const float alpha = 1.f - __expf(-__expf(s == 0 ? sigma0 : sigma1) * (s == 0 ? ax0.y : ax1.y));
+                    const float weight = alpha * T;
+                    const float rr = logistic_d(raw[s][0]), gg = logistic_d(raw[s][1]), bb_ = logistic_d(raw[s][2]);
+                    const float dep = s == 0 ? ax0.x : ax1.x;
+                    cr += rr * weight; cg += gg * weight; cb += bb_ * weight; cd += dep * weight; ca += weight;
+                    if (ca > (1.0f - M.min_transmittance)) {
+                        cr /= ca; cg /= ca; cb /= ca; cd /= ca; ca /= ca;
+                        alive = false; finished = true;
+                    } else if (2 * Q.round + s + 1 >= MARCH_ITER - 1) {      // a live ray of round r has taken 2 r samples
+                        cr = cg = cb = cd = ca = 0.f;                          // never reaches the hit buffer in the reference
+                        alive = false; finished = true;
+                    }
+                }
+            }
+            if (alive && (exits || n_s < 2)) { alive = false; finished = true; }   // ran out of occupied cells
+        }
+        if (valid) {
+            P.res_rgbd[e] = make_float4(cr, cg, cb, cd);
+            P.res_a[e] = ca;
+        }
+        // rays that go on: append to the next round's live list (one atomic per warp)
+        const uint32_t go = __ballot_sync(0xffffffffu, alive);
+        if (go) {
+            const int leader = __ffs(go) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(Q.cnt_out, (uint32_t)__popc(go));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (alive) Q.live_out[base + __popc(go & ((1u << lane) - 1))] = e;
+        }
+        (void)finished;
+        __syncthreads();      // the A tiles are rewritten at the top of the next block
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc<128>(tmem_base); }
+    if (P.n_samples || P.prof) {
+        for (int o = 16; o > 0; o >>= 1) my_samples += __shfl_xor_sync(0xffffffffu, my_samples, o);
+        for (int o = 16; o > 0; o >>= 1) my_rays += __shfl_xor_sync(0xffffffffu, my_rays, o);
+        if ((tid & 31) == 0) {
+            if (P.n_samples && my_samples) atomicAdd(P.n_samples, my_samples);
+            if (P.prof && my_samples) atomicAdd(P.prof, my_samples);
+            if (P.prof && my_rays) atomicAdd(P.prof + 1, my_rays);
+        }
+    }
+}
+
+}  // namespace d2r
