@@ -513,7 +513,10 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     static const bool use_tc = []() { const char* e = getenv("D2R_MARCH"); return !(e && strcmp(e, "simt") == 0); }();
     static const int ctas_per_sm = []() { const char* e = getenv("D2R_MARCH_CTAS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 4 ? v : 4; }();
     static const bool use_solo = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "solo") == 0; }();    // per-thread gathers (no lane pairing)
-    static const bool use_split = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "split") == 0; }();   // round-based gather / MLP kernels
+    // default: round-based gather / MLP kernels (d2r_march_split.cuh); D2R_MARCH=fused|solo|lpi4|tc1|simt select the older kernels
+    static const bool use_split = []() { const char* e = getenv("D2R_MARCH"); return !e || !*e || strcmp(e, "split") == 0; }();
+    static const bool split_coop = []() { const char* e = getenv("D2R_SPLIT_COOP"); return e && atoi(e) != 0; }();
+    static const int split_gctas = []() { const char* e = getenv("D2R_SPLIT_GCTAS"); const int v = e ? atoi(e) : 7; return v >= 1 && v <= 16 ? v : 7; }();
     static const int abl = []() { const char* e = getenv("D2R_MARCH_ABL"); return e ? atoi(e) : 0; }();   // timing ablations, wrong-free results
     static const bool use_solo4 = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "solo4") == 0; }();
     static const bool use_lpi4 = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "lpi4") == 0; }();    // 4 levels per gather batch
@@ -618,10 +621,11 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
                     Q.round = r;
                     Q.cnt_in = s.sp_cnt + r; Q.cnt_out = s.sp_cnt + r + 1;
                     Q.live_in = s.sp_live[r & 1]; Q.live_out = s.sp_live[(r + 1) & 1];
-                    k_gather_round<<<s.n_sm * 6, 128, 0, stream>>>(P, Q);
+                    if (split_coop) k_gather_round<true><<<s.n_sm * split_gctas, 128, 0, stream>>>(P, Q);
+                    else k_gather_round<false><<<s.n_sm * split_gctas, 128, 0, stream>>>(P, Q);
                     k_mlp_round<<<s.n_sm * 4, TC_THREADS, T2_TOTAL, stream>>>(P, Q);
                     count_launch(2);
-                    if ((r & 7) == 7) {                 // every 8 rounds: is anything left?  (one 4-byte read-back)
+                    if (r >= 7 && (r & 3) == 3) {       // every 4th round from round 7 on: is anything left?  (one 4-byte read-back)
                         uint32_t left = 0;
                         D2R_CUDA(cudaMemcpyAsync(&left, s.sp_cnt + r + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
                         D2R_CUDA(cudaStreamSynchronize(stream));

@@ -32,6 +32,7 @@ struct SplitParams {
 
 constexpr int SPLIT_TILE_BYTES = 128 * 32 * 2;
 
+template <bool COOP>
 __global__ void __launch_bounds__(128, 6) k_gather_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
     const ModelDev& M = P.M;
     const int tid = threadIdx.x;
@@ -41,8 +42,9 @@ __global__ void __launch_bounds__(128, 6) k_gather_round(const __grid_constant__
     unsigned long long my_samples = 0;
     for (uint32_t blk = blockIdx.x; (size_t)blk * 128 < n_live; blk += gridDim.x) {
         const uint32_t i = blk * 128 + tid;
-        if (i >= n_live) continue;
-        const uint32_t e = Q.round == 0 ? i : Q.live_in[i];
+        const bool valid = i < n_live;
+        if (!COOP && !valid) continue;
+        const uint32_t e = !valid ? 0u : (Q.round == 0 ? i : Q.live_in[i]);
         const RayEntry en = P.entries[e];
         const Mat3x4 C = P.cams[en.k];
         RayGeom g;
@@ -61,15 +63,17 @@ __global__ void __launch_bounds__(128, 6) k_gather_round(const __grid_constant__
                 __half2 h = __floats2half2_rn(sh[2 * j], sh[2 * j + 1]);
                 pk[j] = *reinterpret_cast<uint32_t*>(&h);
             }
-            Q.shb[(size_t)i * 2] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            Q.shb[(size_t)i * 2 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            if (valid) {
+                Q.shb[(size_t)i * 2] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                Q.shb[(size_t)i * 2 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
         }
         // the walk of k_march_tc2 (phase B), verbatim
         int n_s = 0;
         bool exits = false;
         float wp0x = 0.f, wp0y = 0.f, wp0z = 0.f, wp1x = 0.f, wp1y = 0.f, wp1z = 0.f;
         float dep0 = 0.f, dep1 = 0.f, dtu0 = 0.f, dtu1 = 0.f;
-        while (true) {
+        while (valid) {
             const float px = g.ox + t * g.dx, py = g.oy + t * g.dy, pz = g.oz + t * g.dz;
             if (t >= MAX_DEPTH() || t > g.t_exit || !raabb_contains(M, px, py, pz)) { exits = true; break; }
             uint32_t mip = min(max(mip_from_pos(px, py, pz), 0u), max_mip);
@@ -94,24 +98,35 @@ __global__ void __launch_bounds__(128, 6) k_gather_round(const __grid_constant__
             while (mip < max_mip && !density_grid_occupied_at(px, py, pz, M.bitfield_lin, mip + 1)) ++mip;
             t = advance_to_next_voxel(t, cone, px, py, pz, g.dx, g.dy, g.dz, g.ix, g.iy, g.iz, mip);
         }
-        Q.t_cur[e] = t;
-        Q.nsb[i] = (uint8_t)(n_s | (exits ? 16 : 0));
-        Q.aux[((size_t)blk * 2 + 0) * 128 + tid] = make_float2(dep0, dtu0);
-        Q.aux[((size_t)blk * 2 + 1) * 128 + tid] = make_float2(dep1, dtu1);
+        if (valid) {
+            Q.t_cur[e] = t;
+            Q.nsb[i] = (uint8_t)(n_s | (exits ? 16 : 0));
+            Q.aux[((size_t)blk * 2 + 0) * 128 + tid] = make_float2(dep0, dtu0);
+            Q.aux[((size_t)blk * 2 + 1) * 128 + tid] = make_float2(dep1, dtu1);
+        }
         my_samples += (unsigned)n_s;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            if (s < n_s) {
+            if (COOP ? __any_sync(0xffffffffu, s < n_s) : (s < n_s)) {
                 const float sx = s ? wp1x : wp0x, sy = s ? wp1y : wp0y, sz = s ? wp1z : wp0z;
+                float pe[3], po[3];
+                if (COOP) {
+                    const int lane_e = (tid & 31) & ~1, lane_o = (tid & 31) | 1;
+                    pe[0] = __shfl_sync(0xffffffffu, sx, lane_e); pe[1] = __shfl_sync(0xffffffffu, sy, lane_e); pe[2] = __shfl_sync(0xffffffffu, sz, lane_e);
+                    po[0] = __shfl_sync(0xffffffffu, sx, lane_o); po[1] = __shfl_sync(0xffffffffu, sy, lane_o); po[2] = __shfl_sync(0xffffffffu, sz, lane_o);
+                }
                 unsigned char* row = Q.feat + ((size_t)blk * 2 + s) * SPLIT_TILE_BYTES + umma_chunk_off(tid, 0, 32);
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     __half2 f[4];
-                    encode_levels<2>(M, 2 * c, sx, sy, sz, f);
-                    uint4 v;
-                    v.x = *reinterpret_cast<uint32_t*>(&f[0]); v.y = *reinterpret_cast<uint32_t*>(&f[1]);
-                    v.z = *reinterpret_cast<uint32_t*>(&f[2]); v.w = *reinterpret_cast<uint32_t*>(&f[3]);
-                    *reinterpret_cast<uint4*>(row + c * 128) = v;
+                    if (COOP) encode_levels_pair<2>(M, 2 * c, sx, sy, sz, pe, po, f);
+                    else encode_levels<2>(M, 2 * c, sx, sy, sz, f);
+                    if (s < n_s) {
+                        uint4 v;
+                        v.x = *reinterpret_cast<uint32_t*>(&f[0]); v.y = *reinterpret_cast<uint32_t*>(&f[1]);
+                        v.z = *reinterpret_cast<uint32_t*>(&f[2]); v.w = *reinterpret_cast<uint32_t*>(&f[3]);
+                        *reinterpret_cast<uint4*>(row + c * 128) = v;
+                    }
                 }
             }
         }
@@ -168,6 +183,15 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
         const int n_s = (int)(ns_raw & 15u);
         const bool exits = (ns_raw & 16u) != 0;
         const uint32_t e = valid ? (Q.round == 0 ? i : Q.live_in[i]) : 0u;
+        {   // the next block's inputs come from HBM (a round's features do not fit the L2): start them towards the L2 now
+            const uint32_t nb = blk + 2 * gridDim.x;            // two blocks ahead (the first two blocks of a CTA go unprefetched)
+            if ((size_t)nb * 128 < n_live) {
+                const unsigned char* f = Q.feat + (size_t)nb * 2 * SPLIT_TILE_BYTES + (size_t)tid * 128;     // 16 KB = 128 lines
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(f));
+                if (tid < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char*>(Q.aux + (size_t)nb * 2 * 128) + tid * 128));
+                else if (tid < 48) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char*>(Q.shb + (size_t)nb * 128 * 2) + (tid - 16) * 128));
+            }
+        }
         // this slot's rows of the two sample tiles: already in operand layout, 4 x 16 bytes each
         {
             const unsigned char* src = Q.feat + (size_t)blk * 2 * SPLIT_TILE_BYTES + umma_chunk_off(tid, 0, 32);
