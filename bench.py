@@ -260,10 +260,11 @@ def run_ours(args):
         "e2e": {"value": total * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(K * 12 * 4),
                 "d2h_bytes_per_step": int(K * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_march (fused ray-march + composite)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "roofline": {"kernel": "ray march (k_gather_round + k_mlp_round, all rounds of a launch; D2R_MARCH=fused: k_march_tc2)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes / max(1, nl.value), "peak_source": peak_src, "launches": int(nl.value),
                      "avg_launch_ms": mm.value / max(1, nl.value), "share_of_step": mm.value / ms,
-                     "note": "algorithmic bytes; both hash tables (~50 MB) are L2-resident so DRAM traffic is far lower (DESIGN.md section 5)"},
+                     "note": "algorithmic bytes (512 B of table reads per sample + 23 B per primary ray); the hash tables (~25 MB) are L2-resident, so DRAM traffic is "
+                             "mostly the fp16 features the two march kernels hand over (DESIGN.md section 5); traffic = ncu dram bytes per launch"},
     }
     from dream2real_b200.clip import CLIP_CONFIGS
     c = CLIP_CONFIGS[args.clip]
