@@ -601,7 +601,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
                     const size_t blocks = (need + 127) / 128;
                     D2R_CUDA(cudaMalloc(&s.sp_feat, blocks * 2 * SPLIT_TILE_BYTES));
                     D2R_CUDA(cudaMalloc(&s.sp_aux, blocks * 2 * 128 * sizeof(float2)));
-                    D2R_CUDA(cudaMalloc(&s.sp_shb, blocks * 128 * 2 * sizeof(uint4)));
+                    D2R_CUDA(cudaMalloc(&s.sp_shb, need * 2 * sizeof(uint4)));
                     D2R_CUDA(cudaMalloc(&s.sp_nsb, blocks * 128));
                     D2R_CUDA(cudaMalloc(&s.sp_t, need * sizeof(float)));
                     D2R_CUDA(cudaMalloc(&s.sp_live[0], need * sizeof(uint32_t)));
@@ -621,8 +621,9 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
                     Q.round = r;
                     Q.cnt_in = s.sp_cnt + r; Q.cnt_out = s.sp_cnt + r + 1;
                     Q.live_in = s.sp_live[r & 1]; Q.live_out = s.sp_live[(r + 1) & 1];
-                    if (split_coop) k_gather_round<true><<<s.n_sm * split_gctas, 128, 0, stream>>>(P, Q);
-                    else k_gather_round<false><<<s.n_sm * split_gctas, 128, 0, stream>>>(P, Q);
+                    if (split_coop) k_gather_round<true, 6><<<s.n_sm * std::min(split_gctas, 6), 128, 0, stream>>>(P, Q);
+                    else if (split_gctas >= 8) k_gather_round<false, 8><<<s.n_sm * 8, 128, 0, stream>>>(P, Q);
+                    else k_gather_round<false, 7><<<s.n_sm * split_gctas, 128, 0, stream>>>(P, Q);
                     k_mlp_round<<<s.n_sm * 4, TC_THREADS, T2_TOTAL, stream>>>(P, Q);
                     count_launch(2);
                     if (r >= 7 && (r & 3) == 3) {       // every 4th round from round 7 on: is anything left?  (one 4-byte read-back)

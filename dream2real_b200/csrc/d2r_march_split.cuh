@@ -25,15 +25,15 @@ struct SplitParams {
     uint32_t* live_out;
     unsigned char* feat;        // [block][2][8 KB]: sample tile = 128 rows x 32 fp16 in UMMA canonical K-major layout
     float2* aux;                // [block][2][128]: (depth of the sample, unwarped dt)
-    uint4* shb;                 // [block][128][2]: 16 fp16 SH coefficients of the ray direction
+    uint4* shb;                 // [entries][2]: 16 fp16 SH coefficients of the ray direction (written in round 0)
     uint8_t* nsb;               // [block*128]: samples prepared (0..2) | 16 if the ray leaves the occupied region after them
     float* t_cur;               // [entries]: ray parameter after the samples taken so far
 };
 
 constexpr int SPLIT_TILE_BYTES = 128 * 32 * 2;
 
-template <bool COOP>
-__global__ void __launch_bounds__(128, 6) k_gather_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
+template <bool COOP, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_gather_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
     const ModelDev& M = P.M;
     const int tid = threadIdx.x;
     const uint32_t n_live = Q.round == 0 ? *P.n_entries : *Q.cnt_in;
@@ -48,12 +48,11 @@ __global__ void __launch_bounds__(128, 6) k_gather_round(const __grid_constant__
         const RayEntry en = P.entries[e];
         const Mat3x4 C = P.cams[en.k];
         RayGeom g;
-        float t0, t_box;
-        setup_ray(M, C, __ldg(P.dirs + en.idx), g, t0, t_box);      // same arithmetic as pass 1
+        ray_geom_only(C, __ldg(P.dirs + en.idx), g);                 // same arithmetic as pass 1 (setup_ray)
         g.t_exit = en.t_exit;
         float t = Q.round == 0 ? en.t : Q.t_cur[e];
         const float fwx = C.c[2][0], fwy = C.c[2][1], fwz = C.c[2][2];
-        {
+        if (Q.round == 0 && valid) {          // SH coefficients of the ray direction: once per ray, kept by entry id
             float sh[16];
             const float wx = (g.dx + 1.0f) * 0.5f, wy = (g.dy + 1.0f) * 0.5f, wz = (g.dz + 1.0f) * 0.5f;
             sh_enc4(wx * 2.f - 1.f, wy * 2.f - 1.f, wz * 2.f - 1.f, sh);
@@ -63,10 +62,8 @@ __global__ void __launch_bounds__(128, 6) k_gather_round(const __grid_constant__
                 __half2 h = __floats2half2_rn(sh[2 * j], sh[2 * j + 1]);
                 pk[j] = *reinterpret_cast<uint32_t*>(&h);
             }
-            if (valid) {
-                Q.shb[(size_t)i * 2] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                Q.shb[(size_t)i * 2 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            }
+            Q.shb[(size_t)e * 2] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            Q.shb[(size_t)e * 2 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
         // the walk of k_march_tc2 (phase B), verbatim
         int n_s = 0;
@@ -189,7 +186,6 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
                 const unsigned char* f = Q.feat + (size_t)nb * 2 * SPLIT_TILE_BYTES + (size_t)tid * 128;     // 16 KB = 128 lines
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(f));
                 if (tid < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char*>(Q.aux + (size_t)nb * 2 * 128) + tid * 128));
-                else if (tid < 48) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char*>(Q.shb + (size_t)nb * 128 * 2) + (tid - 16) * 128));
             }
         }
         // this slot's rows of the two sample tiles: already in operand layout, 4 x 16 bytes each
@@ -213,7 +209,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
         uint4 sh0 = make_uint4(0, 0, 0, 0), sh1 = sh0;
         float2 ax0 = make_float2(0.f, 0.f), ax1 = ax0;
         if (valid) {
-            sh0 = Q.shb[(size_t)i * 2]; sh1 = Q.shb[(size_t)i * 2 + 1];
+            sh0 = Q.shb[(size_t)e * 2]; sh1 = Q.shb[(size_t)e * 2 + 1];
             ax0 = Q.aux[((size_t)blk * 2 + 0) * 128 + tid];
             ax1 = Q.aux[((size_t)blk * 2 + 1) * 128 + tid];
         }

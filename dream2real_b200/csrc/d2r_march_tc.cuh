@@ -77,6 +77,21 @@ struct TcRay {
     uint32_t sh[8];      // 16 fp16 SH coefficients
 };
 
+// origin, normalised direction and its reciprocal only: the first part of setup_ray, same arithmetic (the hit list
+// already holds what the box / sphere tests produce)
+__device__ __forceinline__ void ray_geom_only(const Mat3x4& C, float2 dc, RayGeom& r) {
+    float vx = 0.f, vy = 0.f, vz = 0.f;
+    vx += C.c[0][0] * dc.x; vy += C.c[0][1] * dc.x; vz += C.c[0][2] * dc.x;
+    vx += C.c[1][0] * dc.y; vy += C.c[1][1] * dc.y; vz += C.c[1][2] * dc.y;
+    vx += C.c[2][0] * 1.0f; vy += C.c[2][1] * 1.0f; vz += C.c[2][2] * 1.0f;
+    float len2 = 0.f;
+    len2 += vx * vx; len2 += vy * vy; len2 += vz * vz;
+    const float len = sqrtf(len2);
+    r.dx = vx / len; r.dy = vy / len; r.dz = vz / len;
+    r.ox = C.c[3][0]; r.oy = C.c[3][1]; r.oz = C.c[3][2];
+    r.ix = 1.0f / r.dx; r.iy = 1.0f / r.dy; r.iz = 1.0f / r.dz;
+}
+
 // primary-ray set-up shared by k_classify and the slot refill: init_rays_with_payload_kernel_nerf
 // (NGP testbed_nerf.cu:1394-1482).  Returns false when the ray can never take a sample.
 __device__ __forceinline__ bool setup_ray(const ModelDev& M, const Mat3x4& C, float2 dc, RayGeom& r, float& t, float& t_box) {
