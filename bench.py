@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--poses", type=int, default=4096)
     ap.add_argument("--res", type=int, default=800)
     ap.add_argument("--clip", default="ViT-B/32", choices=["ViT-B/32", "ViT-L/14-336"])
-    ap.add_argument("--chunk", type=int, default=512)
+    ap.add_argument("--chunk", type=int, default=1024)
     ap.add_argument("--log2-hashmap", type=int, default=19)
     ap.add_argument("--cpu-sample", type=int, default=2, help="candidates per CPU-baseline sample / reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -241,8 +241,9 @@ def run_ours(args):
     traffic = None
     try:
         summ = json.load(open(os.path.join(ROOT, "profiles", "march_ncu_summary.json")))
-        if summ.get("candidates_per_launch") == args.chunk and summ.get("resolution") == res and args.scene == summ.get("scene"):
-            traffic = summ["dram_bytes_per_launch"]
+        if summ.get("resolution") == res and args.scene == summ.get("scene"):
+            # captured on a 512-candidate launch; candidates are independent, so a launch of `chunk` candidates moves chunk/512 x as much
+            traffic = summ["dram_bytes_per_launch"] * min(args.chunk, K) / summ["candidates_per_launch"]
     except Exception:
         pass
     total = K * world

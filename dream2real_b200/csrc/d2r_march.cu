@@ -41,6 +41,7 @@ struct MarchParams {
     int K;
     const int4* bbox;              // per candidate: x0, y0, x1, y1 (inclusive), x1 < x0 = empty
     const uint32_t* tile_prefix;   // [K+1]
+    const uint16_t* tile_cand;     // [total tiles]: candidate of every tile (saves the binary search over tile_prefix)
     uint32_t* counter;             // work-queue head
     float bg[4];                   // Testbed.background_color of the rendered model (sRGB + alpha)
     float4* rgba_out;              // [K,H,W] or null   (Shade)
@@ -324,7 +325,7 @@ __global__ void k_candidate_bbox(int K, int W, int H, const Mat3x4* __restrict__
                                  const float* __restrict__ row_hi, const float occ_min_x, const float occ_min_y,
                                  const float occ_min_z, const float occ_max_x, const float occ_max_y, const float occ_max_z,
                                  int /*unused*/, int4* __restrict__ bbox, uint32_t* __restrict__ tiles) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;     // one warp per candidate
     if (k >= K) return;
     int x0 = 0, y0 = 0, x1 = W - 1, y1 = H - 1;
     {
@@ -343,17 +344,22 @@ __global__ void k_candidate_bbox(int K, int W, int H, const Mat3x4* __restrict__
             const float u = __fdiv_rn(cx, cz), v = __fdiv_rn(cy, cz);
             u0 = fminf(u0, u); u1 = fmaxf(u1, u); v0 = fminf(v0, v); v1 = fmaxf(v1, v);
         }
-        if (!behind) {
+        if (!behind) {      // (uniform across the warp: every lane did the same arithmetic)
             const float eu = 1e-4f * (1.f + fmaxf(fabsf(u0), fabsf(u1))), ev = 1e-4f * (1.f + fmaxf(fabsf(v0), fabsf(v1)));
             u0 -= eu; u1 += eu; v0 -= ev; v1 += ev;
             x0 = W; x1 = -1; y0 = H; y1 = -1;
-            for (int x = 0; x < W; ++x) if (col_hi[x] >= u0 && col_lo[x] <= u1) { x0 = min(x0, x); x1 = max(x1, x); }
-            for (int y = 0; y < H; ++y) if (row_hi[y] >= v0 && row_lo[y] <= v1) { y0 = min(y0, y); y1 = max(y1, y); }
+            for (int x = lane; x < W; x += 32) if (col_hi[x] >= u0 && col_lo[x] <= u1) { x0 = min(x0, x); x1 = max(x1, x); }
+            for (int y = lane; y < H; y += 32) if (row_hi[y] >= v0 && row_lo[y] <= v1) { y0 = min(y0, y); y1 = max(y1, y); }
+            for (int o = 16; o > 0; o >>= 1) {
+                x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+                y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+            }
             if (x1 >= x0 && y1 >= y0) {
                 x0 = max(x0 - 1, 0); y0 = max(y0 - 1, 0); x1 = min(x1 + 1, W - 1); y1 = min(y1 + 1, H - 1);
             }
         }
     }
+    if (lane != 0) return;
     uint32_t n = 0;
     if (x1 >= x0 && y1 >= y0) {
         n = (uint32_t)((x1 - x0 + TILE_W) / TILE_W) * (uint32_t)((y1 - y0 + TILE_H) / TILE_H);
@@ -383,6 +389,11 @@ __global__ void k_tile_prefix(int K, const uint32_t* __restrict__ tiles, uint32_
     for (int i = b; i < e; ++i) { prefix[i] = run; run += tiles[i]; }
     if (tid == 1023) prefix[K] = s[1023];
     if (tid == 0) *counter = 0;
+}
+
+__global__ void k_tile_map(int K, const uint32_t* __restrict__ prefix, uint16_t* __restrict__ map) {
+    const int k = blockIdx.x;
+    for (uint32_t t = prefix[k] + threadIdx.x; t < prefix[k + 1]; t += blockDim.x) map[t] = (uint16_t)k;
 }
 
 // Every frame starts as a copy of the composited background (u8) / the constant background blend (float);
@@ -443,6 +454,7 @@ struct Scratch {   // per-device scratch reused across calls (grown on demand)
     float* ranges = nullptr; int capWH = 0; const void* ranges_view = nullptr;
     uint8_t* bg_u8 = nullptr; size_t cap_bg = 0;
     RayEntry* entries = nullptr; size_t cap_entries = 0; uint32_t* entry_counters = nullptr;
+    uint16_t* tile_cand = nullptr; size_t cap_tile_cand = 0;
     float4* res_rgbd = nullptr; float* res_a = nullptr;
     int n_sm = 0;
     // round-based split path (k_gather_round / k_mlp_round)
@@ -484,6 +496,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
                  unsigned long long* n_samples, cudaStream_t stream, int* rects_out = nullptr, uint8_t* bg_u8_out = nullptr) {
     D2R_REQUIRE(m && v && cams_ngp_host && bg, "render: null argument");
     D2R_REQUIRE(K > 0, "render: K must be positive");
+    D2R_REQUIRE(K <= 65535, "render: at most 65535 candidates per launch");
     D2R_REQUIRE(m->device == v->device && m->device < 16, "render: model and view live on different devices");
     D2R_REQUIRE(rgba_out || depth_out || u8_out, "render: no output requested");
     D2R_REQUIRE(!u8_out || (bg_rgba && bg_depth), "render_composite: background buffers missing");
@@ -521,7 +534,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     static const bool use_solo4 = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "solo4") == 0; }();
     static const bool use_lpi4 = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "lpi4") == 0; }();    // 4 levels per gather batch
     static const bool use_tc1 = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "tc1") == 0; }();   // one sample per round
-    k_candidate_bbox<<<(K + 127) / 128, 128, 0, stream>>>(K, W, H, s.cams, col_lo, col_hi, row_lo, row_hi, M.occ_min[0], M.occ_min[1],
+    k_candidate_bbox<<<(K * 32 + 127) / 128, 128, 0, stream>>>(K, W, H, s.cams, col_lo, col_hi, row_lo, row_hi, M.occ_min[0], M.occ_min[1],
                                                           M.occ_min[2], M.occ_max[0], M.occ_max[1], M.occ_max[2], 0, s.bbox, s.tiles);
     k_tile_prefix<<<1, 1024, 0, stream>>>(K, s.tiles, s.prefix, s.counter);
     count_launch(2);
@@ -548,6 +561,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     for (int i = 0; i < 4; ++i) P.bg[i] = bg[i];
     P.rgba_out = (float4*)rgba_out; P.depth_out = (float4*)depth_out; P.bg_rgba = (const float4*)bg_rgba; P.bg_depth = bg_depth;
     P.u8_out = u8_out; P.n_samples = n_samples;
+    P.tile_cand = nullptr;
     P.entries = nullptr; P.n_entries = nullptr; P.entry_cursor = nullptr; P.res_rgbd = nullptr; P.res_a = nullptr;
     static bool attr_set[16] = {false};
     if (!attr_set[m->device]) {
@@ -587,12 +601,19 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
             D2R_CUDA(cudaMalloc(&s.res_a, need * sizeof(float)));
             s.cap_entries = need;
         }
+        if (total_tiles > s.cap_tile_cand) {
+            if (s.tile_cand) D2R_CUDA(cudaFree(s.tile_cand));
+            D2R_CUDA(cudaMalloc(&s.tile_cand, (size_t)total_tiles * sizeof(uint16_t)));
+            s.cap_tile_cand = total_tiles;
+        }
         D2R_CUDA(cudaMemsetAsync(s.entry_counters, 0, 2 * sizeof(uint32_t), stream));
         P.entries = s.entries; P.n_entries = s.entry_counters; P.entry_cursor = s.entry_counters + 1;
         P.res_rgbd = s.res_rgbd; P.res_a = s.res_a;
+        P.tile_cand = s.tile_cand;
         if (total_tiles) {
+            k_tile_map<<<K, 64, 0, stream>>>(K, s.prefix, s.tile_cand);
             k_classify<<<total_tiles, CTA, 0, stream>>>(P);
-            count_launch();
+            count_launch(2);
             if (evp) D2R_CUDA(cudaEventRecord(evp->first, stream));   // time the march kernel alone
             if (use_split) {
                 if (need > s.cap_split) {

@@ -143,12 +143,7 @@ __global__ void __launch_bounds__(128) k_classify(const __grid_constant__ MarchP
     const ModelDev& M = P.M;
     const int tid = threadIdx.x;
     const uint32_t tile = blockIdx.x;
-    int lo = 0, hi = P.K;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (P.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
-    }
-    const int k = lo;
+    const int k = (int)P.tile_cand[tile];
     const int4 bb = P.bbox[k];
     const uint32_t local = tile - P.tile_prefix[k];
     const int tiles_x = (bb.z - bb.x + TILE_W) / TILE_W;
