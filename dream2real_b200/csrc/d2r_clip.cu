@@ -44,6 +44,43 @@ namespace d2r {
 template <typename OUT>
 __device__ __forceinline__ void warp_layernorm_row(const float* __restrict__ in, int d, const float* __restrict__ w,
                                                    const float* __restrict__ b, float eps, OUT* __restrict__ out, int lane) {
+    if ((d & 127) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        // vector path: a lane owns 4 consecutive columns of every 128-column group (float4 loads, 8/16-byte stores)
+        float4 v[8];
+        const int n = d / 128;   // d <= 1024
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < n) { v[i] = *reinterpret_cast<const float4*>(in + i * 128 + lane * 4); s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / (float)d;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < n) {
+                const float a = v[i].x - mean, b2 = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+                q += (a * a + b2 * b2) + (c * c + e * e);
+            }
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q / (float)d + eps);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < n) {
+                const int c = i * 128 + lane * 4;
+                const float4 ww = *reinterpret_cast<const float4*>(w + c), bb = *reinterpret_cast<const float4*>(b + c);
+                const float y0 = (v[i].x - mean) * rstd * ww.x + bb.x, y1 = (v[i].y - mean) * rstd * ww.y + bb.y;
+                const float y2 = (v[i].z - mean) * rstd * ww.z + bb.z, y3 = (v[i].w - mean) * rstd * ww.w + bb.w;
+                if constexpr (sizeof(OUT) == 2) {
+                    __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    *reinterpret_cast<uint2*>(out + c) = pk;
+                } else {
+                    *reinterpret_cast<float4*>(out + c) = make_float4(y0, y1, y2, y3);
+                }
+            }
+        return;
+    }
     float v[32];
     const int n = d / 32;   // d <= 1024, multiple of 32
     float s = 0.f;
