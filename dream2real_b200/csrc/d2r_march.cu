@@ -469,6 +469,7 @@ static int ensure_scratch(int device, int K, int W, int H) {
     Scratch& s = g_scratch[device];
     if (K > s.capK) {
         cudaFree(s.cams); cudaFree(s.bbox); cudaFree(s.tiles); cudaFree(s.prefix);
+        s.cams = nullptr; s.bbox = nullptr; s.tiles = nullptr; s.prefix = nullptr; s.capK = 0;
         D2R_CUDA(cudaMalloc(&s.cams, (size_t)K * sizeof(Mat3x4)));
         D2R_CUDA(cudaMalloc(&s.bbox, (size_t)K * sizeof(int4)));
         D2R_CUDA(cudaMalloc(&s.tiles, (size_t)K * sizeof(uint32_t)));
@@ -479,11 +480,13 @@ static int ensure_scratch(int device, int K, int W, int H) {
     if (!s.entry_counters) D2R_CUDA(cudaMalloc(&s.entry_counters, 2 * sizeof(uint32_t)));
     if (W + H > s.capWH) {
         cudaFree(s.ranges);
+        s.ranges = nullptr; s.capWH = 0;
         D2R_CUDA(cudaMalloc(&s.ranges, (size_t)2 * (W + H) * sizeof(float)));
         s.capWH = W + H; s.ranges_view = nullptr;
     }
     if ((size_t)W * H * 3 > s.cap_bg) {
         cudaFree(s.bg_u8);
+        s.bg_u8 = nullptr; s.cap_bg = 0;
         D2R_CUDA(cudaMalloc(&s.bg_u8, (size_t)W * H * 3));
         s.cap_bg = (size_t)W * H * 3;
     }
@@ -595,14 +598,16 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
         D2R_CUDA(cudaStreamSynchronize(stream));
         const size_t need = (size_t)total_tiles * CTA;
         if (need > s.cap_entries) {
-            if (s.entries) { D2R_CUDA(cudaFree(s.entries)); D2R_CUDA(cudaFree(s.res_rgbd)); D2R_CUDA(cudaFree(s.res_a)); }
+            if (s.entries) { cudaFree(s.entries); cudaFree(s.res_rgbd); cudaFree(s.res_a); }
+            s.entries = nullptr; s.res_rgbd = nullptr; s.res_a = nullptr; s.cap_entries = 0;
             D2R_CUDA(cudaMalloc(&s.entries, need * sizeof(RayEntry)));
             D2R_CUDA(cudaMalloc(&s.res_rgbd, need * sizeof(float4)));
             D2R_CUDA(cudaMalloc(&s.res_a, need * sizeof(float)));
             s.cap_entries = need;
         }
         if (total_tiles > s.cap_tile_cand) {
-            if (s.tile_cand) D2R_CUDA(cudaFree(s.tile_cand));
+            if (s.tile_cand) cudaFree(s.tile_cand);
+            s.tile_cand = nullptr; s.cap_tile_cand = 0;
             D2R_CUDA(cudaMalloc(&s.tile_cand, (size_t)total_tiles * sizeof(uint16_t)));
             s.cap_tile_cand = total_tiles;
         }
@@ -619,6 +624,9 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
                 if (need > s.cap_split) {
                     cudaFree(s.sp_feat); cudaFree(s.sp_aux); cudaFree(s.sp_shb); cudaFree(s.sp_nsb); cudaFree(s.sp_t);
                     cudaFree(s.sp_live[0]); cudaFree(s.sp_live[1]);
+                    s.sp_feat = nullptr; s.sp_aux = nullptr; s.sp_shb = nullptr; s.sp_nsb = nullptr; s.sp_t = nullptr;
+                    s.sp_live[0] = s.sp_live[1] = nullptr;
+                    s.cap_split = 0;       // a failed allocation below must not leave a stale capacity behind
                     const size_t blocks = (need + 127) / 128;
                     D2R_CUDA(cudaMalloc(&s.sp_feat, blocks * 2 * SPLIT_TILE_BYTES));
                     D2R_CUDA(cudaMalloc(&s.sp_aux, blocks * 2 * 128 * sizeof(float2)));
