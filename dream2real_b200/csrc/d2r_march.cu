@@ -531,6 +531,10 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     static const bool use_solo = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "solo") == 0; }();    // per-thread gathers (no lane pairing)
     // default: round-based gather / MLP kernels (d2r_march_split.cuh); D2R_MARCH=fused|solo|lpi4|tc1|simt select the older kernels
     static const bool use_split = []() { const char* e = getenv("D2R_MARCH"); return !e || !*e || strcmp(e, "split") == 0; }();
+    // launches with few rays (a single background frame, small test renders) would spend their time on ~40 pairs of tiny
+    // round kernels: below this many screen-rectangle rays the fused kernel (one launch, same results) takes them
+    static const bool split_forced = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "split") == 0; }();
+    constexpr size_t SPLIT_MIN_RAYS = 1u << 20;
     static const bool split_coop = []() { const char* e = getenv("D2R_SPLIT_COOP"); return e && atoi(e) != 0; }();
     static const int split_gctas = []() { const char* e = getenv("D2R_SPLIT_GCTAS"); const int v = e ? atoi(e) : 7; return v >= 1 && v <= 16 ? v : 7; }();
     static const int abl = []() { const char* e = getenv("D2R_MARCH_ABL"); return e ? atoi(e) : 0; }();   // timing ablations, wrong-free results
@@ -620,7 +624,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
             k_classify<<<total_tiles, CTA, 0, stream>>>(P);
             count_launch(2);
             if (evp) D2R_CUDA(cudaEventRecord(evp->first, stream));   // time the march kernel alone
-            if (use_split) {
+            if (use_split && (split_forced || need >= SPLIT_MIN_RAYS)) {
                 if (need > s.cap_split) {
                     cudaFree(s.sp_feat); cudaFree(s.sp_aux); cudaFree(s.sp_shb); cudaFree(s.sp_nsb); cudaFree(s.sp_t);
                     cudaFree(s.sp_live[0]); cudaFree(s.sp_live[1]);
