@@ -74,10 +74,11 @@ class renderer:
         if want_depth:
             bg_depth = depth[0, :, :, 0].contiguous()
         else:
-            d = self.rectify_depth(depth_gt, self.resolution)
+            # combined_rendering.py:104-111 uses channel 0 of the 4-channel rectified depth only: skip the repeat
+            d = self._rectify_depth_1ch(depth_gt, self.resolution)
             m = self.rectify_mask(movable_mask, self.resolution)
-            d[m == 0, 0] = 100
-            bg_depth = torch.from_numpy(np.ascontiguousarray(d[..., 0])).to(bg_image.device)
+            np.putmask(d, m == 0, np.float32(100))
+            bg_depth = torch.from_numpy(np.ascontiguousarray(d)).to(bg_image.device)
         return bg_image, bg_depth
 
     # ---- the hot loop ---------------------------------------------------------------------------
@@ -140,11 +141,19 @@ class renderer:
             return img[(h - w) // 2:(h - w) // 2 + w, :]
         return img[:, (w - h) // 2:(w - h) // 2 + h]
 
-    def rectify_depth(self, depth_ori, resolution):
+    def _rectify_depth_1ch(self, depth_ori, resolution):
         import cv2
-        img = self._center_crop(depth_ori.cpu().numpy()).astype(np.float32)
-        depth_clip = cv2.resize(img, (resolution[0], resolution[1]), interpolation=cv2.INTER_CUBIC)
-        return np.repeat(np.expand_dims(depth_clip, axis=2), 4, axis=2)
+        import torch
+        if getattr(depth_ori, "is_cuda", False):
+            # crop and widen fp16 -> fp32 on the GPU (exact) before the copy to the host: numpy's software half
+            # conversion of the frame costs more than the resize itself
+            img = np.ascontiguousarray(self._center_crop(depth_ori).to(torch.float32).cpu().numpy())
+        else:
+            img = self._center_crop(depth_ori.cpu().numpy()).astype(np.float32)
+        return cv2.resize(img, (resolution[0], resolution[1]), interpolation=cv2.INTER_CUBIC)
+
+    def rectify_depth(self, depth_ori, resolution):
+        return np.repeat(np.expand_dims(self._rectify_depth_1ch(depth_ori, resolution), axis=2), 4, axis=2)
 
     def rectify_mask(self, mask_ori, resolution):
         import cv2
