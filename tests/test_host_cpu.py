@@ -207,3 +207,37 @@ def test_composite_oracle_semantics():
     assert tuple(out[0, 1]) == (s(0.2),) * 3
     assert tuple(out[1, 0]) == (0, 0, 0)
     assert tuple(out[1, 1]) == (s(0.2),) * 3                # fg depth 0 -> 100, not < bg 100
+
+
+def test_optimise_pose_grid_argument_errors():
+    """Argument checks that must fire before any device work (reference: use_vis_pcds selects the point-cloud ablation
+    renderer, clip_scoring.py:118-131, which is not on the accelerated path)."""
+    import pytest
+    from dream2real_b200 import clip_scoring
+    with pytest.raises(NotImplementedError):
+        clip_scoring.optimise_pose_grid(None, None, [0], None, "/tmp", use_vis_pcds=True)
+    with pytest.raises(ValueError):
+        clip_scoring.optimise_pose_grid(None, None, [0, 1], None, "/tmp", multi_view="median")
+
+
+def test_background_depth_rectification_matches_reference_recipe():
+    """renderer.render_background's host recipe (centre crop, cv2 INTER_CUBIC resize, 100 m where the mask is 0;
+    combined_rendering.py:104-111,166-209) against the literal 4-channel formulation of the reference."""
+    import cv2
+    import torch
+    from dream2real_b200.reconstruction.combined_rendering import renderer
+    r = renderer.__new__(renderer)
+    r.resolution = [96, 96]
+    g = torch.Generator().manual_seed(3)
+    depth = (torch.rand(72, 128, generator=g) * 2).half()
+    mask = torch.rand(72, 128, generator=g) > 0.2
+    # reference formulation
+    crop = depth.numpy()[:, 28:100].astype(np.float32)
+    d4 = np.repeat(np.expand_dims(cv2.resize(crop, (96, 96), interpolation=cv2.INTER_CUBIC), axis=2), 4, axis=2)
+    m = cv2.resize(mask.numpy()[:, 28:100].astype(np.uint8), (96, 96), interpolation=cv2.INTER_CUBIC)
+    d4[m == 0, 0] = 100
+    # ours
+    d1 = r._rectify_depth_1ch(depth, r.resolution)
+    np.putmask(d1, r.rectify_mask(mask, r.resolution) == 0, np.float32(100))
+    assert np.array_equal(d1, d4[..., 0])
+    assert np.array_equal(r.rectify_depth(depth, r.resolution)[..., 2], cv2.resize(crop, (96, 96), interpolation=cv2.INTER_CUBIC))
