@@ -535,6 +535,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     // round kernels: below this many screen-rectangle rays the fused kernel (one launch, same results) takes them
     static const bool split_forced = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "split") == 0; }();
     constexpr size_t SPLIT_MIN_RAYS = 1u << 20;
+    static const bool split_mlp_old = []() { const char* e = getenv("D2R_SPLIT_MLP"); return e && strcmp(e, "old") == 0; }();
     static const bool split_coop = []() { const char* e = getenv("D2R_SPLIT_COOP"); return e && atoi(e) != 0; }();
     static const int split_gctas = []() { const char* e = getenv("D2R_SPLIT_GCTAS"); const int v = e ? atoi(e) : 7; return v >= 1 && v <= 16 ? v : 7; }();
     static const int abl = []() { const char* e = getenv("D2R_MARCH_ABL"); return e ? atoi(e) : 0; }();   // timing ablations, wrong-free results
@@ -645,7 +646,8 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
                 D2R_CUDA(cudaMemsetAsync(s.sp_cnt, 0, (SPLIT_MAX_ROUNDS + 2) * sizeof(uint32_t), stream));
                 static bool split_attr[16] = {false};
                 if (!split_attr[m->device]) {
-                    D2R_CUDA(cudaFuncSetAttribute(k_mlp_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
+                    D2R_CUDA(cudaFuncSetAttribute(k_mlp_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
+                    D2R_CUDA(cudaFuncSetAttribute(k_mlp_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
                     split_attr[m->device] = true;
                 }
                 SplitParams Q;
@@ -657,7 +659,8 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
                     if (split_coop) k_gather_round<true, 6><<<s.n_sm * std::min(split_gctas, 6), 128, 0, stream>>>(P, Q);
                     else if (split_gctas >= 8) k_gather_round<false, 8><<<s.n_sm * 8, 128, 0, stream>>>(P, Q);
                     else k_gather_round<false, 7><<<s.n_sm * split_gctas, 128, 0, stream>>>(P, Q);
-                    k_mlp_round<<<s.n_sm * 4, TC_THREADS, T2_TOTAL, stream>>>(P, Q);
+                    if (split_mlp_old) k_mlp_round<false><<<s.n_sm * 4, TC_THREADS, T2_TOTAL, stream>>>(P, Q);
+                    else k_mlp_round<true><<<s.n_sm * 4, TC_THREADS, T2_TOTAL, stream>>>(P, Q);
                     count_launch(2);
                     if (r >= 7 && (r & 3) == 3) {       // every 4th round from round 7 on: is anything left?  (one 4-byte read-back)
                         uint32_t left = 0;

@@ -126,11 +126,19 @@ __global__ void __launch_bounds__(128, MINB) k_gather_round(const __grid_constan
                     }
                 }
             }
+            if (valid && s >= n_s) {      // no such sample: a zero row, so that k_mlp_round can fetch rows before it knows n_s
+                unsigned char* row = Q.feat + ((size_t)blk * 2 + s) * SPLIT_TILE_BYTES + umma_chunk_off(tid, 0, 32);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(row + c * 128) = make_uint4(0, 0, 0, 0);
+            }
         }
     }
     (void)my_samples;
 }
 
+// FAST: feature rows are fetched without waiting for the per-ray sample count, and a block's live-list append is
+// finished during the next block's first MMA wait (the atomic's round trip is off the critical path)
+template <bool FAST>
 __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
     extern __shared__ __align__(128) unsigned char smem[];
     const ModelDev& M = P.M;
@@ -173,6 +181,15 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
         tc_commit(mbar);
     };
 
+    uint32_t pend_go = 0, pend_base = 0, pend_e = 0;      // FAST: the previous block's live-list append, atomic already issued
+    bool pend_alive = false;
+    auto flush_append = [&]() {
+        if (pend_go) {
+            const uint32_t base = __shfl_sync(0xffffffffu, pend_base, __ffs(pend_go) - 1);
+            if (pend_alive) Q.live_out[base + __popc(pend_go & ((1u << lane) - 1))] = pend_e;
+            pend_go = 0;
+        }
+    };
     for (uint32_t blk = blockIdx.x; (size_t)blk * 128 < n_live; blk += gridDim.x) {
         const uint32_t i = blk * 128 + tid;
         const bool valid = i < n_live;
@@ -196,7 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint4 v = make_uint4(0, 0, 0, 0);
-                    if (s < n_s) v = *reinterpret_cast<const uint4*>(src + s * SPLIT_TILE_BYTES + c * 128);
+                    if (FAST ? valid : (s < n_s)) v = *reinterpret_cast<const uint4*>(src + s * SPLIT_TILE_BYTES + c * 128);
                     *reinterpret_cast<uint4*>(rowA32 + s * T2_TILE + c * 128) = v;
                 }
             }
@@ -219,6 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
         __syncthreads();
         // ---- density layer 0: 32 -> 64, ReLU ----
         if (tid == 0) { tc_fence_after(); issue2(a32, T2_TILE, wd0, 32, 64); }
+        if (FAST) flush_append();          // the previous block's append: its atomic returned long ago
         mbar_wait(mbar, phase); phase ^= 1;
         tc_fence_after();
 #pragma unroll 1
@@ -342,12 +360,17 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
             const int leader = __ffs(go) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(Q.cnt_out, (uint32_t)__popc(go));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (alive) Q.live_out[base + __popc(go & ((1u << lane) - 1))] = e;
+            if (FAST) {
+                pend_go = go; pend_base = base; pend_alive = alive; pend_e = e;      // finished by flush_append()
+            } else {
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (alive) Q.live_out[base + __popc(go & ((1u << lane) - 1))] = e;
+            }
         }
         (void)finished;
         __syncthreads();      // the A tiles are rewritten at the top of the next block
     }
+    if (FAST) flush_append();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) { tc_fence_after(); tmem_dealloc<128>(tmem_base); }
