@@ -1,4 +1,4 @@
-// Fused NeRF ray-march kernel (sm_100a): ray generation -> occupancy DDA -> hash-grid encode ->
+// NeRF ray march for K candidate cameras (sm_100a): ray generation -> occupancy DDA -> hash-grid encode ->
 // density + colour MLPs -> transmittance compositing (colour AND depth in one pass) -> shade /
 // tonemap epilogue -> optional depth-test composite against a cached background + sRGB/u8 pack.
 //
@@ -8,10 +8,14 @@
 //  kernel_sh, extract_density, composite_kernel_nerf, shade_kernel_nerf; src/render_buffer.cu:
 //  228-262, 529-561) plus the NumPy compositing of reconstruction/combined_rendering.py:133-155.
 //
-// Work decomposition: every candidate gets a conservative screen rectangle that contains every
-// pixel whose ray can touch an occupied density-grid cell; rectangles are cut into 16x8 tiles and
-// the tiles of all candidates form one global queue drained by a persistent grid (one atomic per
-// tile, no host round trips, MLP weights staged in shared memory once per CTA).
+// Work decomposition (launch_march below): every candidate gets a conservative screen rectangle that contains every
+// pixel whose ray can touch an occupied density-grid cell; rectangles are cut into 16x8 tiles; k_classify walks every
+// tile pixel to its first occupied sample and builds the hit list; then either
+//   * rounds of k_gather_round + k_mlp_round (d2r_march_split.cuh; the default for launches of >= 2^20 rays), or
+//   * one persistent fused kernel, k_march_tc2 / k_march_tc (d2r_march_tc2.cuh, d2r_march_tc.cuh), that refills ray slots
+//     from the hit list (small launches; D2R_MARCH=fused|solo|lpi4|tc1 force a variant), or
+//   * k_march, the round-1 CUDA-core bring-up kernel in this file (D2R_MARCH=simt),
+// take the rays to the end, and k_finish turns the per-ray accumulators into pixels.
 #include <algorithm>
 #include <vector>
 
