@@ -192,3 +192,16 @@ def test_multi_view_scoring_is_the_mean_over_views(tmp_path):
     assert torch.allclose(both, (per_view[0] + per_view[1]) / 2, rtol=1e-5, atol=1e-6)
     _, _, mx = clip_scoring.optimise_pose_grid(r, tm.depths[:2], [0, 1], tm, d, multi_view="max", **kw)
     assert torch.allclose(mx, torch.maximum(per_view[0], per_view[1]), rtol=1e-5, atol=1e-6)
+
+
+def test_round_kernels_forced_on_small_renders():
+    """Small launches take the fused kernel by default; D2R_MARCH=split forces k_gather_round / k_mlp_round on them too.
+    The mode is read once per process, so the golden-render parity tests run again in a child process."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, D2R_MARCH="split")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_render_gpu.py"), "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
