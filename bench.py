@@ -2,14 +2,15 @@
 """Benchmark of Dream2Real's imagination-and-scoring hot path (BASELINE.json metric:
 candidate renders + CLIP scores per second at 800x800).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--scene shopping] [--poses 4096] [--res 800] [--clip ViT-B/32] [--chunk 512]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C1|C2|C3|C4|C5]
+                    [--scene shopping] [--poses 4096] [--res 800] [--clip ViT-B/32] [--chunk 1024]
 
 One "step" = one pass of the hot path over one batch of synthetic candidate poses: fused fg render +
 depth-test composite -> rot90 + PIL-exact preprocess -> ViT forward on tcgen05 -> score.
-N = 1 workload = BASELINE.json configs[1] (shopping scene stand-in, 4096 poses, 800x800, 1 x B200);
-N > 1: every rank gets its own 4096 poses (weak scaling) and the ranks exchange scores with one NCCL
-all-gather per step.  Prints ONE JSON line (rank 0).
+--config picks a BASELINE.json configuration; the default is C2 = configs[1] (shopping scene stand-in,
+4096 poses, 800x800, 1 x B200) for N = 1, 2, 4 -- every rank gets its own 4096 poses (weak scaling) -- and C4 (shelf scene,
+6-DoF grid of 65 536 poses sharded 8192 per rank) for N = 8, whose line also carries the C2-per-rank weak-scaling figure
+as `weak_scaling_same_workload`.  The ranks exchange scores with one NCCL all-gather per step.  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -26,6 +27,14 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 METRIC = "candidate renders+CLIP-scores/sec @800x800"
+# BASELINE.json configs as concrete synthetic inputs; poses = per-GPU count at the named GPU count
+CONFIGS = {
+    "C1": dict(scene="shopping", grid=[8, 8, 1, 1, 1, 1], poses=64, res=400, gpus=1),
+    "C2": dict(scene="shopping", grid=[64, 64, 1, 1, 1, 1], poses=4096, res=800, gpus=1),
+    "C3": dict(scene="pool_triangle", grid=[128, 128, 1, 1, 1, 1], poses=16384, res=800, gpus=1),
+    "C4": dict(scene="shelf", grid=[16, 4, 16, 4, 4, 4], poses=65536, res=800, gpus=8),
+    "C5": dict(scene="synthetic8", grid=[64, 64, 1, 4, 4, 4], poses=262144, res=1024, gpus=8),
+}
 UNIT = "candidates/s"
 GOAL = "an apple inside a blue and white bowl"          # reference lang/cache.json (shopping demo)
 NORM = ["an apple and a blue and white bowl"]
@@ -37,30 +46,54 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scene", default="shopping")
-    ap.add_argument("--poses", type=int, default=4096)
-    ap.add_argument("--res", type=int, default=800)
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
+    ap.add_argument("--scene", default=None)
+    ap.add_argument("--poses", type=int, default=None, help="candidate poses per GPU")
+    ap.add_argument("--res", type=int, default=None)
     ap.add_argument("--clip", default="ViT-B/32", choices=["ViT-B/32", "ViT-L/14-336"])
     ap.add_argument("--chunk", type=int, default=1024)
     ap.add_argument("--log2-hashmap", type=int, default=19)
-    ap.add_argument("--cpu-sample", type=int, default=2, help="candidates per CPU-baseline sample / reference step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="candidates per CPU-baseline sample / reference step (0 = one per host core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-secondary", action="store_true", help="N = 8 default run: skip the C2-per-rank weak-scaling figure")
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    explicit = a.config is not None or a.scene is not None or a.poses is not None or a.res is not None
+    if a.config is None:
+        a.config = "C4" if (world == 8 and not explicit) else "C2"
+    a.default_run = not explicit
+    c = CONFIGS[a.config]
+    a.scene = a.scene or c["scene"]
+    a.res = a.res or c["res"]
+    a.grid = c["grid"]
+    if a.poses is None:
+        # C2 is quoted per GPU (weak scaling); C4 / C5 are fixed-size grids sharded over the ranks that run them
+        a.poses = c["poses"] if c["gpus"] == 1 else max(1, c["poses"] // max(world, 1))
+    a.sharded = c["gpus"] > 1
+    return a
 
 
-def pose_grid(scene, n):
-    """First n poses of sample_poses_grid([g, g, 1, 1, 1, 1]) for the scene type (x slowest), g = ceil(sqrt(n))."""
+def pose_grid(scene, n, grid=None, rank=0, world=1, sharded=False):
+    """Candidate poses of this rank: sample_poses_grid(grid) for the scene type (x slowest ... z-rotation fastest).
+    sharded: the contiguous shard `rank` of the full grid (clip_scoring.shard_bounds); else the first n poses (repeated if the
+    grid is smaller), which the caller offsets per rank."""
     import types
 
     import torch
 
+    from dream2real_b200.clip_scoring import shard_bounds
     from dream2real_b200.vision_3d.obj_pose_opt import sample_poses_grid
-    g = int(np.ceil(np.sqrt(n)))
+    if grid is None:
+        g = int(np.ceil(np.sqrt(n)))
+        grid = [g, g, 1, 1, 1, 1] if scene["scene_type"] != 1 else [max(2, int(round(n ** (1 / 3)))) for _ in range(3)] + [1, 1, 1]
     tm = types.SimpleNamespace(scene_model=types.SimpleNamespace(scene_centre=torch.tensor(scene["scene_centre"]), device=torch.device("cpu")))
-    res = [g, g, 1, 1, 1, 1] if scene["scene_type"] != 1 else [max(2, int(round(n ** (1 / 3)))) for _ in range(3)] + [1, 1, 1]
-    p = sample_poses_grid(tm, res, scene_type=scene["scene_type"])
-    reps = int(np.ceil(n / p.shape[0]))
-    return p.repeat(reps, 1)[:n].reshape(-1, 4, 4).numpy().astype(np.float64), res
+    p = sample_poses_grid(tm, grid, scene_type=scene["scene_type"])
+    if sharded:
+        lo, hi = shard_bounds(p.shape[0], world, rank)
+        p = p[lo:hi]
+        n = min(n, p.shape[0]) if p.shape[0] else n
+    reps = int(np.ceil(n / max(1, p.shape[0])))
+    return p.repeat(reps, 1)[:n].reshape(-1, 4, 4).numpy().astype(np.float64), grid
 
 
 class ClockSampler:
@@ -96,7 +129,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_world(args, device, scene_dir):
+def build_world(args, device, scene_dir, scene_name=None):
     """Scene, models, CLIP and cached background -- everything that is per query, not per candidate."""
     import torch
 
@@ -104,7 +137,7 @@ def build_world(args, device, scene_dir):
     from dream2real_b200.clip import ClipVision, make_hf_clip, text_embeds
     from dream2real_b200.reconstruction.combined_rendering import renderer
     from dream2real_b200.utils import accio2ngp
-    scene = synth.make_scene(args.scene, scene_dir, log2_hashmap_size=args.log2_hashmap, seed=1234)
+    scene = synth.make_scene(scene_name or args.scene, scene_dir, log2_hashmap_size=args.log2_hashmap, seed=1234)
     tm = synth.SyntheticTaskModel(scene, GOAL, NORM, device)
     rnd = renderer(scene_dir, tm, resolution=args.res, max_candidates_per_launch=args.chunk)
     hf = make_hf_clip(args.clip, seed=1234, vocab_size=49408)
@@ -116,24 +149,34 @@ def build_world(args, device, scene_dir):
     return scene, tm, rnd, hf, cv, txt, accio2ngp
 
 
-def run_ours(args):
+def march_sources_sha1():
+    """content hash of the march kernel sources: ties a committed ncu traffic summary to the code it was captured on"""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "dream2real_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.startswith("d2r_march") or f in ("d2r_common.cuh", "d2r_gemm.cuh"):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
+
+
+def measure(args, world_ctx, scene_name, K, grid, sharded, steps, warmup, sample_clocks=True):
+    """Device-resident value, e2e value, march roofline and ViT roofline of one workload on this rank set."""
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
     from dream2real_b200 import _native as N
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    rank, world, local, device = world_ctx
     scene_dir = tempfile.mkdtemp(prefix=f"d2r_bench_r{rank}_")
-    scene, tm, rnd, hf, cv, txt, accio2ngp = build_world(args, device, scene_dir)
-    K, res = args.poses, args.res
-    poses, grid_res = pose_grid(scene, K)
-    # every rank scores its own candidate set (weak scaling): shift the grid a little per rank
-    poses[:, 0, 3] += 0.003 * rank
+    scene, tm, rnd, hf, cv, txt, accio2ngp = build_world(args, device, scene_dir, scene_name)
+    res = args.res
+    poses, grid_res = pose_grid(scene, K, grid, rank, world, sharded)
+    K = poses.shape[0]
+    if not sharded:
+        # every rank scores its own candidate set (weak scaling): shift the grid a little per rank
+        poses[:, 0, 3] += 0.003 * rank
     valid_poses_ngp = accio2ngp.converter(poses)
     render_poses_ngp = accio2ngp.converter(scene["opt_cam_poses"][:1])
     fg = tm.movable_obj.vis_model
@@ -170,15 +213,13 @@ def run_ours(args):
     pinned_poses = torch.from_numpy(valid_poses_ngp).pin_memory()
     host_scores = torch.empty(K, dtype=torch.float32).pin_memory()
 
-    from dream2real_b200.clip_scoring import score_renders
-
     def step_e2e():
-        """public API with HOST buffers, the way optimise_pose_grid drives it: poses in pinned host memory ->
-        renderer.render (one call: background once, all candidates) -> score_renders -> scores back on the host."""
+        """public API with HOST buffers, the way optimise_pose_grid drives it: poses in pinned host memory -> renderer.iter_render
+        (background once, then per chunk: fused render+composite -> preprocess -> ViT -> score) -> scores back on the host."""
         vp = pinned_poses.numpy()
-        out = rnd.render(vp, render_poses_ngp, [0], tm.depths[:1], tm.movable_masks, save=False, return_tensor=True)
-        scores.copy_(score_renders(out, cv, txt, n_goal=1, bg_u8=rnd.last_bg_u8, rects=rnd.last_rects))
-        del out
+        for _, s, e, frames, rc, bgu in rnd.iter_render(vp, render_poses_ngp, [0], tm.depths[:1], tm.movable_masks, save=False, chunk=args.chunk):
+            emb = cv.encode_images(frames, rot90=True, bg_u8=bgu, rects=rc)
+            scores[s:e] = cv.score(emb, txt, n_goal=1)
         if world > 1:
             dist.all_gather_into_tensor(gathered, scores)
         host_scores.copy_(scores, non_blocking=True)
@@ -189,11 +230,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, n):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
-        for _ in range(steps):
+        for _ in range(n):
             fn()
         ev1.record()
         barrier()
@@ -202,29 +243,54 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_resident()
     N.check(N.lib().d2r_profile_enable(local, 1))
     N.launch_count(reset=True)
     clocks = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and sample_clocks:
         clocks.start()
     vit_events.clear()
-    ms = timed(step_resident, args.steps)
+    ms = timed(step_resident, steps)
     vit_ms = sum(a.elapsed_time(b) for a, b in vit_events)
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop() if (rank == 0 and sample_clocks) else None
     launches = N.launch_count()
-    import ctypes as C
     mm, nl, ns, nt = C.c_float(), C.c_int(), C.c_ulonglong(), C.c_ulonglong()
     N.check(N.lib().d2r_profile_read(local, C.byref(mm), C.byref(nl), C.byref(ns), C.byref(nt)))
     N.check(N.lib().d2r_profile_enable(local, 0))
     step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, steps)
+    tot = torch.tensor([K], device=device, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(tot)
+    total = int(tot.item())
+    return dict(scene=scene, scene_dir=scene_dir, K=K, total=total, grid=grid_res, ms=ms, ms_e2e=ms_e2e, vit_ms=vit_ms, clocks=clk,
+                launches=int(launches), march_ms=float(mm.value), march_launches=int(nl.value), samples=int(ns.value), rays=int(nt.value))
 
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    ctx = (rank, world, local, device)
+    res, steps = args.res, args.steps
+    m = measure(args, ctx, args.scene, args.poses, args.grid, args.sharded, steps, args.warmup)
+    secondary = None
+    if args.default_run and args.config == "C4" and not args.no_secondary:
+        # the N = 1, 2, 4 lines are C2 per rank: the same workload at this N, so the scaling series stays comparable
+        c2 = CONFIGS["C2"]
+        secondary = measure(args, ctx, c2["scene"], c2["poses"], c2["grid"], False, steps, args.warmup, sample_clocks=False)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    K = m["K"]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -233,39 +299,54 @@ def run_ours(args):
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     # algorithmic bytes of the march kernel: 512 B of hash-table reads per network
     # sample + 23 B per primary ray it owns (20 B cached background rgba+depth read, 3 B u8 written)
-    rays = int(nt.value)          # primary rays (pixels of the candidates' screen rectangles) the kernel owned
-    alg_bytes = int(ns.value) * 512 + rays * 23
-    march_s = mm.value / 1e3
+    rays = m["rays"]          # primary rays (hit-list entries) the kernel owned
+    alg_bytes = m["samples"] * 512 + rays * 23
+    march_s = m["march_ms"] / 1e3
     achieved = alg_bytes / march_s / 1e9 if march_s > 0 else 0.0
-    # DRAM traffic of one march launch from the committed ncu --set full capture of the same launch shape (profiles/)
-    traffic = None
+    # DRAM / L2 traffic of one march launch: ncu capture of the same launch shape, committed under profiles/ together with the
+    # hash of the kernel sources it was taken on -- a capture of other code is refused, not quoted
+    traffic = l2_traffic = None
+    traffic_note = "no ncu capture committed for this workload"
     try:
         summ = json.load(open(os.path.join(ROOT, "profiles", "march_ncu_summary.json")))
-        if summ.get("resolution") == res and args.scene == summ.get("scene"):
-            # captured on a 512-candidate launch; candidates are independent, so a launch of `chunk` candidates moves chunk/512 x as much
-            traffic = summ["dram_bytes_per_launch"] * min(args.chunk, K) / summ["candidates_per_launch"]
+        if summ.get("source_sha1") != march_sources_sha1():
+            traffic_note = "profiles/march_ncu_summary.json was captured on other kernel sources (source_sha1 mismatch): not quoted"
+        elif summ.get("resolution") == res and m["scene"]["name"] == summ.get("scene"):
+            # candidates are independent, so a launch of `chunk` candidates moves chunk / captured-candidates x as much
+            f = min(args.chunk, K) / summ["candidates_per_launch"]
+            traffic = summ["dram_bytes_per_launch"] * f
+            l2_traffic = summ.get("lts_bytes_per_launch", 0) * f or None
+            traffic_note = "ncu dram__bytes_read+write.sum / lts__t_bytes.sum of k_march_ws, scaled to this launch size (profiles/march_ncu_summary.json)"
     except Exception:
         pass
-    total = K * world
-    value = total * args.steps / (ms / 1e3)
+    total = m["total"]
+    value = total * steps / (m["ms"] / 1e3)
+    launches_per_step = max(1, m["march_launches"] // max(1, steps))
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": m["ms"] / steps, "higher_is_better": True, "scaling": "strong" if args.sharded else "weak", "vs_baseline": None,
         "dtype": "f16 (fp16 operands, fp32 accumulate; fp32 residual/softmax/LayerNorm)", "data": "synthetic",
-        "config": {"workload": f"{args.scene} scene stand-in, {K} candidate poses per GPU, {res}x{res}, CLIP {args.clip} random-init, "
-                               f"{world} x B200", "poses_per_gpu": K, "resolution": res, "clip": args.clip, "chunk": args.chunk,
-                   "pose_grid": grid_res, "hash_table": f"2^{args.log2_hashmap}", "l2": "inputs larger than L2 (each chunk's u8 frames "
-                   f"= {args.chunk * res * res * 3 / 1e6:.0f} MB)", "samples_per_candidate": int(ns.value) / max(1, K * args.steps),
-                   "rays_marched_per_candidate": rays / max(1, K * args.steps)},
-        "clocks": clk,
-        "e2e": {"value": total * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(K * 12 * 4),
-                "d2h_bytes_per_step": int(K * 4), "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches),
-        "roofline": {"kernel": "ray march (k_gather_round + k_mlp_round, all rounds of a launch; D2R_MARCH=fused: k_march_tc2)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes / max(1, nl.value), "peak_source": peak_src, "launches": int(nl.value),
-                     "avg_launch_ms": mm.value / max(1, nl.value), "share_of_step": mm.value / ms,
-                     "note": "algorithmic bytes (512 B of table reads per sample + 23 B per primary ray); the hash tables (~25 MB) are L2-resident, so DRAM traffic is "
-                             "mostly the fp16 features the two march kernels hand over (DESIGN.md section 5); traffic = ncu dram bytes per launch"},
+        "config": {"workload": f"{args.config}: {m['scene']['name']} scene stand-in, "
+                               + (f"{total} candidate poses (pose grid {m['grid']}) sharded over {world} x B200, {K} per GPU" if args.sharded
+                                  else f"{K} candidate poses per GPU (pose grid {m['grid']}), {world} x B200")
+                               + f", {res}x{res}, CLIP {args.clip} random-init",
+                   "baseline_config": args.config, "poses_per_gpu": K, "poses_total": total, "resolution": res, "clip": args.clip, "chunk": args.chunk,
+                   "pose_grid": m["grid"], "hash_table": f"2^{args.log2_hashmap}", "l2": "inputs larger than L2 (each chunk's u8 frames "
+                   f"= {min(args.chunk, K) * res * res * 3 / 1e6:.0f} MB)", "samples_per_candidate": m["samples"] / max(1, K * steps),
+                   "rays_marched_per_candidate": rays / max(1, K * steps)},
+        "clocks": m["clocks"],
+        "e2e": {"value": total * steps / (m["ms_e2e"] / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(K * 12 * 4),
+                "d2h_bytes_per_step": int(K * 4), "ms_per_step": m["ms_e2e"] / steps,
+                "path": "renderer.iter_render -> ClipVision.encode_images -> ClipVision.score per chunk (what optimise_pose_grid runs), pinned host poses in, pinned host scores out"},
+        "gpu_launches": m["launches"],
+        "roofline": {"kernel": "k_march_ws (the ray march of one launch of `chunk` candidates: one persistent warp-specialised kernel)", "bound": "hbm",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "l2_traffic": l2_traffic,
+                     "traffic_note": traffic_note, "algorithmic_bytes_per_launch": alg_bytes / max(1, m["march_launches"]), "peak_source": peak_src,
+                     "launches": m["march_launches"], "launches_per_step": launches_per_step,
+                     "avg_launch_ms": m["march_ms"] / max(1, m["march_launches"]), "share_of_step": m["march_ms"] / m["ms"],
+                     "note": "algorithmic bytes (512 B of table reads per sample + 23 B per primary ray); the hash tables (~25 MB) are L2-resident, so "
+                             "the table reads are L2 traffic, not DRAM traffic (SURVEY.md 8(d) caveat): `traffic` (DRAM) and `l2_traffic` (lts) are the "
+                             "measured bytes per launch next to the algorithmic figure"},
     }
     from dream2real_b200.clip import CLIP_CONFIGS
     c = CLIP_CONFIGS[args.clip]
@@ -274,16 +355,27 @@ def run_ours(args):
     d_, mlp_ = c["hidden"], c["mlp"]
     vit_flop = (2.0 * (T - 1) * d_ * kp + c["layers"] * (8.0 * T * d_ * d_ + 4.0 * T * d_ * mlp_ + 4.0 * T * T * d_) + 2.0 * d_ * c["proj"])
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    vit_tf = vit_flop * K * args.steps / (vit_ms / 1e3) / 1e12 if vit_ms > 0 else 0.0
+    vit_tf = vit_flop * K * steps / (m["vit_ms"] / 1e3) / 1e12 if m["vit_ms"] > 0 else 0.0
     out["roofline_vit"] = {"kernel": "CLIP ViT forward (tcgen05 GEMMs + attention + LayerNorm)", "bound": "tensor", "achieved": vit_tf,
                            "peak": tf_peak, "unit": "TFLOP/s", "frac": vit_tf / tf_peak,
                            "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if "bf16_tflops_sustained" in peaks
-                           else "fallback (B200_PROFILING.md)", "gflop_per_image": vit_flop / 1e9, "share_of_step": vit_ms / ms}
+                           else "fallback (B200_PROFILING.md)", "gflop_per_image": vit_flop / 1e9, "share_of_step": m["vit_ms"] / m["ms"]}
+    if secondary is not None:
+        out["weak_scaling_same_workload"] = {
+            "workload": f"C2 per rank: shopping scene stand-in, {secondary['K']} candidate poses per GPU, {res}x{res} -- the workload of the N = 1, 2, 4 lines",
+            "value": secondary["total"] * steps / (secondary["ms"] / 1e3), "unit": UNIT, "ms_per_step": secondary["ms"] / steps,
+            "e2e": secondary["total"] * steps / (secondary["ms_e2e"] / 1e3)}
     if not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args, scene_dir, n=args.cpu_sample)
+        out["cpu_baseline"] = cpu_baseline(args)
     try:
-        out["gpu_reference_context"] = {"what": "reference pyngp Shade+Depth pairs/s on B200 (fox snapshot, render only, no CLIP), tests/golden/pyngp_timing.json",
-                                        **json.load(open(os.path.join(ROOT, "tests", "golden", "pyngp_timing.json")))}
+        t = json.load(open(os.path.join(ROOT, "tests", "golden", "pyngp_synth_timing.json")))
+        r = t.get(str(res), t.get("800"))
+        out["gpu_reference_context"] = {
+            "what": "the reference's own GPU loop on the bench scene, run on a B200 by tests/golden/make_golden_synth.py (not part of this run): per candidate "
+                    "two pyngp renders + NumPy composite (combined_rendering.py:117-155), then CLIPProcessor + HF CLIPModel fp32 in batches of 128 "
+                    "(clip_scoring.py:168-185)", "scene": t.get("scene"), "resolution": res if str(res) in t else 800,
+            "render_composite_ms_per_candidate": r["render_composite_ms_per_candidate"],
+            "candidates_per_s": r.get(args.clip, {}).get("candidates_per_s")}
     except Exception:
         pass
     print(json.dumps(out))
@@ -291,93 +383,132 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_pipeline(args, scene_dir, n):
-    """The reference algorithm restated on the CPU (oracle/): per candidate the NGP march of the movable object
-    (colour + depth from one march, rays that miss the occupied box culled -- two result-preserving shortcuts the
-    reference's two full-frame renders per candidate, combined_rendering.py:123-130, do not take), numpy composite,
-    rot90, PIL preprocessing, HF CLIP fp32."""
+# ---- CPU arm: the reference algorithm restated on the CPU (oracle/), all host cores ---------------------------------------
+_CPU = {}
+
+
+def _cpu_init(scene_name, res, log2_hashmap, scene_dir):
+    """per worker process: scene, snapshots, view table, background render (once per query, like the GPU arm)"""
+    from dream2real_b200 import ingp, synth
+    from oracle import ngp_oracle as O
+    from oracle import post_oracle as PO
+    try:
+        import torch
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+    scene = synth.make_scene(scene_name, scene_dir, log2_hashmap_size=log2_hashmap, seed=1234) if not os.path.exists(os.path.join(scene_dir, "fg_base.ingp")) \
+        else None
+    _CPU["fg"] = ingp.load_snapshot(os.path.join(scene_dir, "fg_base.ingp"))
+    _CPU["vs"] = O.view_setup(_CPU["fg"], 0, res, res)
+    _CPU["dirs"] = O.camera_plane_dirs(_CPU["vs"])
+    _CPU["fgb"], _ = O.build_bitfield(_CPU["fg"].density_grid, _CPU["fg"].max_cascade)
+    _CPU["box"] = O.occupied_box(_CPU["fgb"], _CPU["fg"].max_cascade)
+    del scene
+
+
+def _cpu_render_one(job):
+    """one candidate: NGP march of the movable object (colour + depth from one march, rays that miss the occupied box culled --
+    two result-preserving shortcuts the reference's two full-frame renders per candidate, combined_rendering.py:123-130, do not
+    take) + the NumPy composite"""
+    from oracle import ngp_oracle as O
+    from oracle import post_oracle as PO
+    cam, bg_img, bg_d = job
+    sh, dp = O.render(_CPU["fg"], _CPU["fgb"], _CPU["vs"], cam[:3], both=True, background_color=[0, 0, 0, 0], plane_dirs=_CPU["dirs"], cull_box=_CPU["box"])
+    return PO.composite(bg_img, bg_d, sh, dp[..., 0])
+
+
+def cpu_pipeline(scene_name, grid, n_poses, res, clip_name, log2_hashmap, procs):
+    """Returns step(idx) -> scores for the candidates idx, the render fanned out over `procs` worker processes (one candidate each),
+    then rot90, PIL preprocessing and HF CLIP fp32 on all torch threads."""
+    import multiprocessing as mp
+
     import torch
 
     from dream2real_b200 import ingp, synth
     from dream2real_b200.clip import make_hf_clip
     from oracle import ngp_oracle as O
     from oracle import post_oracle as PO
-    torch.set_num_threads(os.cpu_count() or 1)
-    scene = synth.make_scene(args.scene, scene_dir, log2_hashmap_size=args.log2_hashmap, seed=1234)
-    fg = ingp.load_snapshot(os.path.join(scene_dir, "fg_base.ingp"))
+    scene_dir = tempfile.mkdtemp(prefix="d2r_bench_cpu_")
+    scene = synth.make_scene(scene_name, scene_dir, log2_hashmap_size=log2_hashmap, seed=1234)
     bg = ingp.load_snapshot(os.path.join(scene_dir, "bg_base.ingp"))
-    res = args.res
     vs = O.view_setup(bg, 0, res, res)
     dirs = O.camera_plane_dirs(vs)
-    fgb, _ = O.build_bitfield(fg.density_grid, fg.max_cascade)
     bgb, _ = O.build_bitfield(bg.density_grid, bg.max_cascade)
-    box = O.occupied_box(fgb, fg.max_cascade)
     rp = PO.converter(scene["opt_cam_poses"][:1])
     # once per query (not timed, like the GPU arm): background render + depth, CLIP model, text
     bg_img = O.render(bg, bgb, vs, rp[0][:3], mode=O.SHADE, background_color=[0, 0, 0, 1], plane_dirs=dirs)
     bg_d = PO.background_depth(scene["depths"][0], scene["movable_masks"][0], (res, res))
-    hf = make_hf_clip(args.clip, seed=1234, vocab_size=49408)
+    hf = make_hf_clip(clip_name, seed=1234, vocab_size=49408)
     g = torch.Generator().manual_seed(1234)
     ids = torch.randint(3, 40000, (1 + len(NORM), 12), generator=g)
     ids[:, -1] = 2
-    poses, _ = pose_grid(scene, args.poses)
+    poses, _ = pose_grid(scene, n_poses, grid)
     vp = PO.converter(poses)
     T1 = PO.converter(scene["fg_pose"][None])[0]
     R = hf.config.vision_config.image_size
+    pool = mp.get_context("fork").Pool(procs, initializer=_cpu_init, initargs=(scene_name, res, log2_hashmap, scene_dir)) if procs > 1 else None
+    if pool is None:
+        _cpu_init(scene_name, res, log2_hashmap, scene_dir)
+    torch.set_num_threads(os.cpu_count() or 1)
 
     def step(idx):
-        imgs = []
-        for i in idx:
-            cam = PO.convert_virtual_pose(T1, vp[i], rp[0])
-            # one march for colour and depth and the occupied-box ray cull: both favour the CPU arm
-            sh, dp = O.render(fg, fgb, vs, cam[:3], both=True, background_color=[0, 0, 0, 0], plane_dirs=dirs, cull_box=box)
-            imgs.append(PO.composite(bg_img, bg_d, sh, dp[..., 0]))
+        jobs = [(PO.convert_virtual_pose(T1, vp[i], rp[0]), bg_img, bg_d) for i in idx]
+        imgs = pool.map(_cpu_render_one, jobs, chunksize=1) if pool is not None else [_cpu_render_one(j) for j in jobs]
         imgs = np.rot90(np.stack(imgs), k=1, axes=(1, 2))
         px = PO.clip_preprocess(imgs, R)
         logits = PO.clip_logits(hf, px, ids)
         return PO.normalise_scores(logits, 1)
+    step.close = (lambda: (pool.close(), pool.join())) if pool is not None else (lambda: None)
     return step
 
 
-def cpu_baseline(args, scene_dir, n):
-    step = cpu_pipeline(args, scene_dir, n)
-    stride = max(1, args.poses // n)
-    idx = [(i * stride + stride // 2) % args.poses for i in range(n)]
-    step(idx[:1])
+def cpu_baseline(args):
+    """BASELINE.json configs[0] (C1), exactly: shopping scene, the 64 poses of the 8x8 grid, 400x400, the reference path on the CPU of this
+    box -- oracle render fanned out over all host cores, HF CLIP fp32 on all torch threads."""
+    cores = os.cpu_count() or 1
+    c1 = CONFIGS["C1"]
+    step = cpu_pipeline(c1["scene"], c1["grid"], c1["poses"], c1["res"], args.clip, args.log2_hashmap, cores)
+    step(list(range(min(cores, c1["poses"]))))          # warm the worker processes
     t0 = time.time()
-    step(idx)
+    step(list(range(c1["poses"])))
     dt = time.time() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{n} of the {args.poses} candidates (evenly spaced) at {args.res}x{args.res}, CLIP {args.clip} fp32: numpy oracle render "
-                      f"(single thread; colour+depth in one march, occupied-box ray cull) + HF CLIP on {os.cpu_count()} torch threads; "
-                      "the reference itself has no CPU render path (pyngp is CUDA-only)"}
+    step.close()
+    return {"value": c1["poses"] / dt, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
+            "sample": f"C1 = BASELINE.json configs[0]: shopping scene, all {c1['poses']} poses of the 8x8 grid at {c1['res']}x{c1['res']}, CLIP {args.clip} fp32: "
+                      f"numpy oracle render, one candidate per worker process on {cores} host cores (colour+depth in one march, occupied-box ray cull) + "
+                      f"HF CLIP on {cores} torch threads; the reference itself has no CPU render path (pyngp is CUDA-only)"}
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the reference path on this arm's config (scene, resolution, CLIP), each step a
+    bounded sample of the workload (one candidate per host core unless --cpu-sample says otherwise), all host cores."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    scene_dir = tempfile.mkdtemp(prefix="d2r_bench_ref_")
-    n = args.cpu_sample
-    step = cpu_pipeline(args, scene_dir, n)
-    stride = max(1, args.poses // n)
+    cores = os.cpu_count() or 1
+    n = args.cpu_sample or cores
+    total = int(np.prod(args.grid)) if args.sharded else args.poses
+    step = cpu_pipeline(args.scene, args.grid, total, args.res, args.clip, args.log2_hashmap, min(cores, n))
+    stride = max(1, total // n)
     base = [(i * stride + stride // 2) for i in range(n)]
     for w in range(min(args.warmup, 1)):
-        step([b % args.poses for b in base[:1]])
+        step([b % total for b in base[:min(cores, n)]])
     t0 = time.time()
     for s in range(args.steps):
-        step([(b + 7 * s) % args.poses for b in base])
+        step([(b + 7 * s) % total for b in base])
     dt = time.time() - t0
+    step.close()
     value = n * args.steps / dt
-    sample = (f"each step = {n} of the {args.poses} candidates at {args.res}x{args.res} (bounded sample), CLIP {args.clip} fp32; numpy oracle "
-              f"render (single thread) + HF CLIP on {os.cpu_count()} torch threads")
+    sample = (f"each step = {n} of the {total} candidates at {args.res}x{args.res} (bounded sample, evenly spaced), CLIP {args.clip} fp32; numpy oracle "
+              f"render, one candidate per worker process on {min(cores, n)} of {cores} host cores + HF CLIP on {cores} torch threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (numpy/torch CPU; fp16-emulated NGP network)", "data": "synthetic",
-        "config": {"workload": f"{args.scene} scene stand-in, {args.poses} candidate poses, {args.res}x{args.res}, CLIP {args.clip} random-init, "
-                               "CPU port of the reference path (the reference's renderer is CUDA-only)", "sample_per_step": n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "scaling": "strong" if args.sharded else "weak", "vs_baseline": None, "dtype": "f32 (numpy/torch CPU; fp16-emulated NGP network)", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {args.scene} scene stand-in, {total} candidate poses, {args.res}x{args.res}, CLIP {args.clip} random-init, "
+                               "CPU port of the reference path (the reference's renderer is CUDA-only)", "baseline_config": args.config, "sample_per_step": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 

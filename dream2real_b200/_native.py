@@ -17,8 +17,8 @@ LIB_PATH = os.path.join(_HERE, "libd2r_b200.so")
 EXPORTS = [
     "d2r_model_load", "d2r_model_free", "d2r_model_set_min_transmittance", "d2r_model_get_bitfield", "d2r_model_get_occupied_aabb",
     "d2r_view_prepare", "d2r_view_free", "d2r_view_get_dirs",
-    "d2r_render", "d2r_render_composite", "d2r_render_composite_ex",
-    "d2r_clip_preprocess", "d2r_clip_preprocess_delta", "d2r_clip_load", "d2r_clip_free", "d2r_clip_encode", "d2r_score", "d2r_gemm_f16", "d2r_profile_enable", "d2r_profile_read",
+    "d2r_render", "d2r_render_ex", "d2r_render_composite", "d2r_render_composite_ex",
+    "d2r_clip_preprocess", "d2r_clip_preprocess_delta", "d2r_clip_load", "d2r_clip_free", "d2r_clip_encode", "d2r_score", "d2r_gemm_f16", "d2r_profile_enable", "d2r_profile_read", "d2r_profile_read_stats",
     "d2r_last_error", "d2r_launch_count", "d2r_version",
 ]
 
@@ -69,6 +69,7 @@ def lib():
         "d2r_view_free": (None, [vp]),
         "d2r_view_get_dirs": (i, [vp, vp]),
         "d2r_render": (i, [vp, vp, vp, i, f4, vp, vp, vp, vp]),
+        "d2r_render_ex": (i, [vp, vp, vp, i, f4, vp, vp, vp, vp, vp]),
         "d2r_render_composite": (i, [vp, vp, vp, i, f4, vp, vp, vp, vp, vp]),
         "d2r_render_composite_ex": (i, [vp, vp, vp, i, f4, vp, vp, vp, vp, vp, vp, vp]),
         "d2r_clip_preprocess": (i, [vp, i, i, i, i, i, i, f4, f4, vp, vp, vp]),
@@ -79,6 +80,7 @@ def lib():
         "d2r_score": (i, [vp, vp, i, i, i, C.c_float, i, vp, vp, vp]),
         "d2r_profile_enable": (i, [i, i]),
         "d2r_profile_read": (i, [i, vp, vp, vp, vp]),
+        "d2r_profile_read_stats": (i, [i, vp]),
         "d2r_gemm_f16": (i, [vp, i, vp, i, i, i, i, vp, i, vp, i, vp]),
     }
     assert set(sigs) == set(EXPORTS)

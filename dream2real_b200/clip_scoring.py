@@ -24,22 +24,27 @@ CLIP_NAME = "openai/clip-vit-large-patch14-336"      # clip_scoring.py:150-151
 _clip_cache = {}
 
 
-def _load_clip(clip_model, clip_processor):
+def _load_clip(clip_model, clip_processor, need_processor=True):
+    """clip_scoring.py:150-151; D2R_CLIP_PATH points at a local copy of the checkpoint (there is no network here)."""
+    path = os.environ.get("D2R_CLIP_PATH", CLIP_NAME)
     if clip_model is None:
-        from transformers import CLIPModel, CLIPProcessor
-        path = os.environ.get("D2R_CLIP_PATH", CLIP_NAME)
+        from transformers import CLIPModel
         clip_model = CLIPModel.from_pretrained(path).eval()
-        if clip_processor is None:
-            clip_processor = CLIPProcessor.from_pretrained(path)
+    if clip_processor is None and need_processor:      # also when the caller brought a model but neither a processor nor text_inputs
+        from transformers import CLIPProcessor
+        clip_processor = CLIPProcessor.from_pretrained(path)
     return clip_model, clip_processor
 
 
 def _vision_for(clip_model, device, max_batch):
+    """One vision tower on the device per HF model; the entry keeps the model alive, so its id() cannot be recycled by another."""
     key = (id(clip_model), int(device), int(max_batch))
-    if key not in _clip_cache:
+    hit = _clip_cache.get(key)
+    if hit is None or hit[0] is not clip_model:
         _clip_cache.clear()
-        _clip_cache[key] = d2r_clip.ClipVision(clip_model, max_batch=max_batch, device=device)
-    return _clip_cache[key]
+        hit = (clip_model, d2r_clip.ClipVision(clip_model, max_batch=max_batch, device=device))
+        _clip_cache[key] = hit
+    return hit[1]
 
 
 def shard_bounds(n, world_size, rank):
@@ -108,7 +113,7 @@ def optimise_pose_grid(renderer,
     rank = torch.distributed.get_rank() if dist_on else 0
 
     renders = None
-    frame_bg, frame_rects = None, None
+    stream_args = None
     if use_cache_renders:
         import cv2
         print('Using cached renders')
@@ -134,22 +139,21 @@ def optimise_pose_grid(renderer,
             raise Exception
         if physics_only:
             print('Physics only method')
-            best_pose_idx = torch.randint(valid_idxs.shape[0], (1,)).item()
+            pick = torch.randint(valid_idxs.shape[0], (1,))
+            if dist_on:      # every rank returns the same pose: rank 0's draw
+                pick = pick.to(device)
+                torch.distributed.broadcast(pick, src=0)
+            best_pose_idx = int(pick.item())
             return valid_poses[best_pose_idx].view(4, 4), pose_batch, torch.ones(pose_batch.shape[0])
         render_poses = get_virtual_cam_poses(task_model, render_cam_pose_idx)
         print('Rendering images from ngp...')
         render_poses_ngp = accio2ngp.converter(render_poses)
         valid_poses_ngp = accio2ngp.converter(valid_poses.cpu().numpy().reshape(-1, 4, 4))
         lo, hi = shard_bounds(valid_poses_ngp.shape[0], world, rank)
-        if hi > lo:
-            renders = renderer.render(valid_poses_ngp[lo:hi], render_poses_ngp, render_cam_pose_idx, depths_gt,
-                                      task_model.movable_masks, save=save_renders and world == 1, return_tensor=True)
-            frame_bg, frame_rects = getattr(renderer, "last_bg_u8", None), getattr(renderer, "last_rects", None)
-
-    task_model.free_visual_models()
+        stream_args = (valid_poses_ngp, render_poses_ngp)
 
     print('Evaluating rendered images using CLIP...')
-    clip_model, clip_processor = _load_clip(clip_model, clip_processor)
+    clip_model, clip_processor = _load_clip(clip_model, clip_processor, need_processor=text_inputs is None)
     goal_caption = task_model.goal_caption
     norm_captions = task_model.norm_captions
     n_goal = 1
@@ -171,12 +175,21 @@ def optimise_pose_grid(renderer,
     assert txt.shape[0] == len(captions), "text_inputs must hold one row per caption"
 
     with torch.no_grad():
-        if renders is not None and renders.shape[0] > 0:
-            vision = _vision_for(clip_model, device.index, clip_batch_size)
-            local = score_renders(renders, vision, txt, n_goal=n_goal, bg_u8=frame_bg, rects=frame_rects)
-            if n_views > 1:      # renders are view-major [L*K]: one score per pose = mean (or max) over its L views
-                local = local.view(n_views, -1)
-                local = local.mean(0) if multi_view == "mean" else local.max(0).values
+        vision = _vision_for(clip_model, device.index, clip_batch_size)
+        if stream_args is not None and hi > lo:
+            # render -> preprocess -> encode -> score per chunk: only [n_views, K] scores outlive a chunk (the reference renders
+            # everything first, clip_scoring.py:120-147; at 800x800 its 70 000-pose shopping grid would be 134 GB of frames)
+            valid_poses_ngp, render_poses_ngp = stream_args
+            local = torch.empty((n_views, hi - lo), dtype=torch.float32, device=device)
+            chunk = min(int(getattr(renderer, "max_candidates_per_launch", vision.max_batch)), vision.max_batch)
+            for v, s, e, frames, rects, bg_u8 in renderer.iter_render(valid_poses_ngp[lo:hi], render_poses_ngp, render_cam_pose_idx, depths_gt,
+                                                                      task_model.movable_masks, save=save_renders and world == 1, chunk=chunk):
+                emb = vision.encode_images(frames, rot90=True, bg_u8=bg_u8, rects=rects)
+                local[v, s:e] = vision.score(emb, txt, n_goal=n_goal)
+            # one score per pose = mean (or max) over its L per-view scores
+            local = local[0] if n_views == 1 else (local.mean(0) if multi_view == "mean" else local.max(0).values)
+        elif renders is not None and renders.shape[0] > 0:
+            local = score_renders(renders, vision, txt, n_goal=n_goal)
         else:
             local = torch.zeros(0, dtype=torch.float32, device=device)
         logits = gather_scores(local, valid_idxs.shape[0], world, rank) if world > 1 else local
@@ -196,9 +209,17 @@ def optimise_pose_grid(renderer,
     best_pose_idx = torch.argmax(pose_scores).item()
     best_pose = valid_poses[render_idxs[best_pose_idx]]
     j = int(render_idxs[best_pose_idx])
-    if renders is not None and lo <= j < hi:
+    best_u8 = None
+    if renders is not None:
+        best_u8 = renders[j]
+    elif stream_args is not None and rank == 0:
+        # frames were streamed: render the winner again (a candidate's frame does not depend on its batch, bit for bit)
+        best_u8 = renderer.render(stream_args[0][j:j + 1], stream_args[1][:1], render_cam_pose_idx[:1],
+                                  None if depths_gt is None else depths_gt[:1], task_model.movable_masks, save=False, return_tensor=True)[0]
+    task_model.free_visual_models()
+    if best_u8 is not None:
         from PIL import Image
-        best_render = np.rot90(renders[j - lo].cpu().numpy(), k=1, axes=(0, 1))     # first view of the best pose
+        best_render = np.rot90(best_u8.cpu().numpy(), k=1, axes=(0, 1))     # first view of the best pose
         best_render = Image.fromarray(np.ascontiguousarray(best_render))
         best_render.save(os.path.join(data_dir, 'best_render.png'))
         if show_best:

@@ -34,6 +34,20 @@ inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
         }                                                                                          \
     } while (0)
 
+struct DevBuf {        // temporary device allocation, released on every exit path
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+struct DeviceGuard {   // the library never leaves the caller's current device changed
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) cudaSetDevice(device);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // ---- constants: reference include/neural-graphics-primitives/nerf_device.cuh:23-42 -------------
 constexpr uint32_t NERF_GRIDSIZE = 128;
 constexpr uint32_t NERF_GRID_N_CELLS = 128u * 128u * 128u;
@@ -60,6 +74,7 @@ struct ModelDev {
     const __half* w_c0;  // [64,32]
     const __half* w_c1;  // [64,64]
     const __half* w_c2;  // [16,64]
+    const unsigned char* w_umma;       // the five matrices as UMMA B operands (K-major, no swizzle), 20480 bytes: what the march kernels stage
     const uint8_t* bitfield;           // [8 * 128^3 / 8], Morton order inside a cascade (the reference's layout; exported)
     const uint8_t* bitfield_lin;       // same bits, cell (x,y,z) at bit x + 128*y + 128^2*z: what the march reads (no Morton encode)
     float aabb_min[3], aabb_diag[3];
@@ -82,6 +97,7 @@ struct d2r_model {
     void* params_dev;     // fp16 blob
     uint8_t* bitfield_dev;
     uint8_t* bitfield_lin_dev;
+    void* w_umma_dev;
     size_t n_params;
     d2r_model_cfg cfg;
 };
@@ -91,4 +107,7 @@ struct d2r_view {
     int W, H;
     float2* dirs_dev;     // [H*W] undistorted camera-plane (x, y), z == 1
     d2r_camera cam;
+    // per-column min/max of dirs.x and per-row min/max of dirs.y, [col_lo W | col_hi W | row_lo H | row_hi H]: the host plans
+    // every candidate's conservative screen rectangle from them (launch_march), so no launch needs a read-back
+    float* ranges_host;
 };

@@ -1,8 +1,8 @@
-// Round-based split of the ray march: k_gather_round (walk + hash-grid gather, no barriers, no tensor-core state ->
+// Round-based split of the ray march (D2R_MARCH=split; kept as the A/B partner of k_march_ws): k_gather_round (walk + hash-grid gather, no barriers, no tensor-core state ->
 // few registers, many warps per SM) and k_mlp_round (the five MLP layers on tcgen05 + compositing), alternating until no
-// ray is left.  Included by d2r_march.cu after d2r_march_tc2.cuh (shares its helpers and shared-memory plan).
+// ray is left.  Included by d2r_march.cu after d2r_march_common.cuh.
 //
-// Why: the fused kernel (k_march_tc2) runs at 16 warps per SM -- 128 registers per thread, all TMEM columns, 208 KB of
+// Why (round 1): a fused kernel whose threads do everything runs at 16 warps per SM -- 128 registers per thread, all TMEM columns, 208 KB of
 // shared memory -- and every component's latency (walk, gather, five MMA round trips) is exposed in full: the kernel's time
 // does not depend on the table size (2^14 vs 2^19 entries: same time per sample), doubling the gather adds 55 %, doubling
 // the walk 17 % (profiles/).  The gather needs neither TMEM nor shared memory, so on its own it runs at 3x the occupancy.
@@ -10,7 +10,7 @@
 // kernel stages them with plain 16-byte copies), plus 24 B of per-ray accumulators per round.
 //
 // Per round r every live ray takes its next (up to) two samples -- the same walk, features and compositing arithmetic as
-// k_march_tc2, so the results are identical; a ray that finishes keeps its accumulators in res_rgbd / res_a (k_finish turns
+// k_march_ws, so the results are identical; a ray that finishes keeps its accumulators in res_rgbd / res_a (k_finish turns
 // them into pixels), a ray that continues is appended to the next round's live list.  A live ray of round r has taken
 // exactly 2 r samples, so the reference's step counter needs no storage.
 #pragma once
@@ -32,8 +32,7 @@ struct SplitParams {
 
 constexpr int SPLIT_TILE_BYTES = 128 * 32 * 2;
 
-template <bool COOP, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_gather_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
+__global__ void __launch_bounds__(128, 7) k_gather_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
     const ModelDev& M = P.M;
     const int tid = threadIdx.x;
     const uint32_t n_live = Q.round == 0 ? *P.n_entries : *Q.cnt_in;
@@ -43,7 +42,7 @@ __global__ void __launch_bounds__(128, MINB) k_gather_round(const __grid_constan
     for (uint32_t blk = blockIdx.x; (size_t)blk * 128 < n_live; blk += gridDim.x) {
         const uint32_t i = blk * 128 + tid;
         const bool valid = i < n_live;
-        if (!COOP && !valid) continue;
+        if (!valid) continue;
         const uint32_t e = !valid ? 0u : (Q.round == 0 ? i : Q.live_in[i]);
         const RayEntry en = P.entries[e];
         const Mat3x4 C = P.cams[en.k];
@@ -65,7 +64,7 @@ __global__ void __launch_bounds__(128, MINB) k_gather_round(const __grid_constan
             Q.shb[(size_t)e * 2] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             Q.shb[(size_t)e * 2 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
-        // the walk of k_march_tc2 (phase B), verbatim
+        // the walk of k_march_ws (phase B), verbatim
         int n_s = 0;
         bool exits = false;
         float wp0x = 0.f, wp0y = 0.f, wp0z = 0.f, wp1x = 0.f, wp1y = 0.f, wp1z = 0.f;
@@ -104,29 +103,20 @@ __global__ void __launch_bounds__(128, MINB) k_gather_round(const __grid_constan
         my_samples += (unsigned)n_s;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            if (COOP ? __any_sync(0xffffffffu, s < n_s) : (s < n_s)) {
+            if (s < n_s) {
                 const float sx = s ? wp1x : wp0x, sy = s ? wp1y : wp0y, sz = s ? wp1z : wp0z;
-                float pe[3], po[3];
-                if (COOP) {
-                    const int lane_e = (tid & 31) & ~1, lane_o = (tid & 31) | 1;
-                    pe[0] = __shfl_sync(0xffffffffu, sx, lane_e); pe[1] = __shfl_sync(0xffffffffu, sy, lane_e); pe[2] = __shfl_sync(0xffffffffu, sz, lane_e);
-                    po[0] = __shfl_sync(0xffffffffu, sx, lane_o); po[1] = __shfl_sync(0xffffffffu, sy, lane_o); po[2] = __shfl_sync(0xffffffffu, sz, lane_o);
-                }
                 unsigned char* row = Q.feat + ((size_t)blk * 2 + s) * SPLIT_TILE_BYTES + umma_chunk_off(tid, 0, 32);
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     __half2 f[4];
-                    if (COOP) encode_levels_pair<2>(M, 2 * c, sx, sy, sz, pe, po, f);
-                    else encode_levels<2>(M, 2 * c, sx, sy, sz, f);
-                    if (s < n_s) {
-                        uint4 v;
-                        v.x = *reinterpret_cast<uint32_t*>(&f[0]); v.y = *reinterpret_cast<uint32_t*>(&f[1]);
-                        v.z = *reinterpret_cast<uint32_t*>(&f[2]); v.w = *reinterpret_cast<uint32_t*>(&f[3]);
-                        *reinterpret_cast<uint4*>(row + c * 128) = v;
-                    }
+                    encode_levels<2>(M, 2 * c, sx, sy, sz, f);
+                    uint4 v;
+                    v.x = *reinterpret_cast<uint32_t*>(&f[0]); v.y = *reinterpret_cast<uint32_t*>(&f[1]);
+                    v.z = *reinterpret_cast<uint32_t*>(&f[2]); v.w = *reinterpret_cast<uint32_t*>(&f[3]);
+                    *reinterpret_cast<uint4*>(row + c * 128) = v;
                 }
             }
-            if (valid && s >= n_s) {      // no such sample: a zero row, so that k_mlp_round can fetch rows before it knows n_s
+            if (s >= n_s) {      // no such sample: a zero row, so that k_mlp_round can fetch rows before it knows n_s
                 unsigned char* row = Q.feat + ((size_t)blk * 2 + s) * SPLIT_TILE_BYTES + umma_chunk_off(tid, 0, 32);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(row + c * 128) = make_uint4(0, 0, 0, 0);
@@ -136,9 +126,15 @@ __global__ void __launch_bounds__(128, MINB) k_gather_round(const __grid_constan
     (void)my_samples;
 }
 
-// FAST: feature rows are fetched without waiting for the per-ray sample count, and a block's live-list append is
-// finished during the next block's first MMA wait (the atomic's round trip is off the critical path)
-template <bool FAST>
+// shared memory plan of k_mlp_round (bytes): weights, then 2 tiles whose K=32 and K=64 operands alias (52 KB -> 4 CTAs per SM)
+constexpr int T2_A64 = W_BYTES;
+constexpr int T2_A32 = T2_A64;
+constexpr int T2_TILE = 16384;
+constexpr int T2_MISC = T2_A64 + 2 * T2_TILE;
+constexpr int T2_TOTAL = T2_MISC + 256;
+
+// feature rows are fetched without waiting for the per-ray sample count, and a block's live-list append is finished during
+// the next block's first MMA wait (the atomic's round trip is off the critical path)
 __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
     extern __shared__ __align__(128) unsigned char smem[];
     const ModelDev& M = P.M;
@@ -146,11 +142,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + T2_MISC);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T2_MISC + 8);
 
-    stage_weights(smem + T2_WD0, M.w_d0, 64, 32, tid);
-    stage_weights(smem + T2_WD1, M.w_d1, 16, 64, tid);
-    stage_weights(smem + T2_WC0, M.w_c0, 64, 32, tid);
-    stage_weights(smem + T2_WC1, M.w_c1, 64, 64, tid);
-    stage_weights(smem + T2_WC2, M.w_c2, 16, 64, tid);
+    for (int i = tid; i < W_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(M.w_umma)[i];
     if (tid == 0) { mbar_init(mbar, 1); fence_barrier_init(); }
     if (warp == 0) tmem_alloc<128>(tmem_slot);
     fence_proxy_async();
@@ -160,8 +152,8 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t a32 = smem_u32(smem + T2_A32), a64 = smem_u32(smem + T2_A64);
-    const uint32_t wd0 = smem_u32(smem + T2_WD0), wd1 = smem_u32(smem + T2_WD1), wc0 = smem_u32(smem + T2_WC0),
-                   wc1 = smem_u32(smem + T2_WC1), wc2 = smem_u32(smem + T2_WC2);
+    const uint32_t wd0 = smem_u32(smem + W_D0), wd1 = smem_u32(smem + W_D1), wc0 = smem_u32(smem + W_C0),
+                   wc1 = smem_u32(smem + W_C1), wc2 = smem_u32(smem + W_C2);
     unsigned char* rowA32 = smem + T2_A32 + umma_chunk_off(tid, 0, 32);
     unsigned char* rowA64 = smem + T2_A64 + umma_chunk_off(tid, 0, 64);
     uint32_t phase = 0;
@@ -181,7 +173,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
         tc_commit(mbar);
     };
 
-    uint32_t pend_go = 0, pend_base = 0, pend_e = 0;      // FAST: the previous block's live-list append, atomic already issued
+    uint32_t pend_go = 0, pend_base = 0, pend_e = 0;      // the previous block's live-list append, atomic already issued
     bool pend_alive = false;
     auto flush_append = [&]() {
         if (pend_go) {
@@ -213,7 +205,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint4 v = make_uint4(0, 0, 0, 0);
-                    if (FAST ? valid : (s < n_s)) v = *reinterpret_cast<const uint4*>(src + s * SPLIT_TILE_BYTES + c * 128);
+                    if (valid) v = *reinterpret_cast<const uint4*>(src + s * SPLIT_TILE_BYTES + c * 128);
                     *reinterpret_cast<uint4*>(rowA32 + s * T2_TILE + c * 128) = v;
                 }
             }
@@ -236,7 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
         __syncthreads();
         // ---- density layer 0: 32 -> 64, ReLU ----
         if (tid == 0) { tc_fence_after(); issue2(a32, T2_TILE, wd0, 32, 64); }
-        if (FAST) flush_append();          // the previous block's append: its atomic returned long ago
+        flush_append();          // the previous block's append: its atomic returned long ago
         mbar_wait(mbar, phase); phase ^= 1;
         tc_fence_after();
 #pragma unroll 1
@@ -325,7 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
             tmem_ld_wait();
             raw[s][0] = h2f_round(__uint_as_float(r[0])); raw[s][1] = h2f_round(__uint_as_float(r[1])); raw[s][2] = h2f_round(__uint_as_float(r[2]));
         }
-        // ---- composite_kernel_nerf (testbed_nerf.cu:511-667), sample 0 then sample 1; same arithmetic as k_march_tc2 ----
+        // ---- composite_kernel_nerf (testbed_nerf.cu:511-667), sample 0 then sample 1; same arithmetic as k_march_ws ----
         bool alive = valid;
         bool finished = false;
         if (alive) {
@@ -360,17 +352,12 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
             const int leader = __ffs(go) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(Q.cnt_out, (uint32_t)__popc(go));
-            if (FAST) {
-                pend_go = go; pend_base = base; pend_alive = alive; pend_e = e;      // finished by flush_append()
-            } else {
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (alive) Q.live_out[base + __popc(go & ((1u << lane) - 1))] = e;
-            }
+            pend_go = go; pend_base = base; pend_alive = alive; pend_e = e;      // finished by flush_append()
         }
         (void)finished;
         __syncthreads();      // the A tiles are rewritten at the top of the next block
     }
-    if (FAST) flush_append();
+    flush_append();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) { tc_fence_after(); tmem_dealloc<128>(tmem_base); }

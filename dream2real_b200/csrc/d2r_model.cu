@@ -151,6 +151,22 @@ __global__ void k_view_dirs(int W, int H, float fx, float fy, float scx, float s
     out[x + W * y] = make_float2(dx, dy);
 }
 
+// per-column min/max of the direction table's x and per-row min/max of its y: with them a candidate's conservative screen
+// rectangle follows from the projection of the occupied box, lens distortion included (launch_march plans it on the host)
+__global__ void k_view_ranges(int W, int H, const float2* __restrict__ dirs, float* col_lo, float* col_hi, float* row_lo, float* row_hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < W) {
+        float lo = 1e30f, hi = -1e30f;
+        for (int y = 0; y < H; ++y) { const float v = dirs[i + W * y].x; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+        col_lo[i] = lo; col_hi[i] = hi;
+    }
+    if (i < H) {
+        float lo = 1e30f, hi = -1e30f;
+        for (int x = 0; x < W; ++x) { const float v = dirs[x + W * i].y; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+        row_lo[i] = lo; row_hi[i] = hi;
+    }
+}
+
 }  // namespace d2r
 
 using namespace d2r;
@@ -163,15 +179,13 @@ extern "C" unsigned long long d2r_launch_count(int reset) {
 }
 extern "C" const char* d2r_version(void) { return "d2r_b200 0.1 (sm_100a)"; }
 
-extern "C" int d2r_model_load(const void* params_f16_host, size_t n_params, const float* density_grid_f32_host,
-                              size_t n_grid_cells, const d2r_model_cfg* cfg, int device, d2r_model** out) {
-    D2R_REQUIRE(params_f16_host && density_grid_f32_host && cfg && out, "d2r_model_load: null argument");
+static int model_load_impl(const void* params_f16_host, size_t n_params, const float* density_grid_f32_host,
+                           size_t n_grid_cells, const d2r_model_cfg* cfg, int device, d2r_model* m) {
     D2R_REQUIRE(cfg->n_levels == 8 && cfg->n_features_per_level == 4,
                 "d2r_model_load: only the Dream2Real NGP config (8 levels x 4 features) is supported");
     D2R_REQUIRE(cfg->max_cascade >= 0 && cfg->max_cascade < (int)NERF_CASCADES, "d2r_model_load: bad max_cascade");
     D2R_REQUIRE(n_grid_cells == (size_t)NERF_GRID_N_CELLS * (cfg->max_cascade + 1),
                 "Incompatible number of grid cascades.");   // testbed.cu:4811-4814
-    D2R_CUDA(cudaSetDevice(device));
 
     // hash-grid offsets: GridEncodingTemplated ctor (tiny-cuda-nn grid.h:693-722), host math
     uint32_t offsets[MAX_LEVELS + 1];
@@ -197,8 +211,6 @@ extern "C" int d2r_model_load(const void* params_f16_host, size_t n_params, cons
         return D2R_ERR_INVALID;
     }
 
-    d2r_model* m = new d2r_model();
-    memset(m, 0, sizeof(*m));
     m->device = device;
     m->cfg = *cfg;
     m->n_params = n_params;
@@ -209,10 +221,11 @@ extern "C" int d2r_model_load(const void* params_f16_host, size_t n_params, cons
     D2R_CUDA(cudaMalloc(&m->bitfield_lin_dev, bf_bytes));
 
     // occupancy bitfield
-    float* grid_dev = nullptr;
-    double* mean_dev = nullptr;
-    D2R_CUDA(cudaMalloc(&grid_dev, n_grid_cells * sizeof(float)));
-    D2R_CUDA(cudaMalloc(&mean_dev, sizeof(double)));
+    DevBuf grid_buf, mean_buf, scale_buf, res_buf;
+    D2R_CUDA(cudaMalloc(&grid_buf.p, n_grid_cells * sizeof(float)));
+    D2R_CUDA(cudaMalloc(&mean_buf.p, sizeof(double)));
+    float* grid_dev = (float*)grid_buf.p;
+    double* mean_dev = (double*)mean_buf.p;
     D2R_CUDA(cudaMemcpy(grid_dev, density_grid_f32_host, n_grid_cells * sizeof(float), cudaMemcpyHostToDevice));
     D2R_CUDA(cudaMemset(mean_dev, 0, sizeof(double)));
     const uint32_t n = NERF_GRID_N_CELLS;
@@ -227,15 +240,15 @@ extern "C" int d2r_model_load(const void* params_f16_host, size_t n_params, cons
     D2R_CUDA(cudaGetLastError());
 
     // level geometry on device
-    float* scale_dev; uint32_t* res_dev;
-    D2R_CUDA(cudaMalloc(&scale_dev, MAX_LEVELS * sizeof(float)));
-    D2R_CUDA(cudaMalloc(&res_dev, MAX_LEVELS * sizeof(uint32_t)));
+    D2R_CUDA(cudaMalloc(&scale_buf.p, MAX_LEVELS * sizeof(float)));
+    D2R_CUDA(cudaMalloc(&res_buf.p, MAX_LEVELS * sizeof(uint32_t)));
+    float* scale_dev = (float*)scale_buf.p;
+    uint32_t* res_dev = (uint32_t*)res_buf.p;
     k_level_geometry<<<1, 32>>>(cfg->n_levels, std::log2(cfg->per_level_scale), (uint32_t)cfg->base_resolution, scale_dev, res_dev);
     count_launch();
     ModelDev& d = m->dev;
     D2R_CUDA(cudaMemcpy(d.level_scale, scale_dev, MAX_LEVELS * sizeof(float), cudaMemcpyDeviceToHost));
     D2R_CUDA(cudaMemcpy(d.level_res, res_dev, MAX_LEVELS * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    cudaFree(scale_dev); cudaFree(res_dev);
     memcpy(d.level_offset, offsets, sizeof(offsets));
     for (int l = 0; l < cfg->n_levels; ++l) {
         // the reference's stride loop (tiny-cuda-nn common_device.h:697-713) decides dense vs hashed per level
@@ -253,6 +266,26 @@ extern "C" int d2r_model_load(const void* params_f16_host, size_t n_params, cons
         }
     }
 
+    {   // MLP weights re-arranged once as UMMA B operands (canonical K-major, no swizzle: 8x8 core matrices of 128 contiguous
+        // bytes, core matrices adjacent in K 128 B apart, 8-row groups K/8*128 B apart), in the order the kernels' W_* offsets expect
+        const __half* hp = (const __half*)params_f16_host;
+        std::vector<__half> blob(20480 / 2);
+        const int shp[5][2] = {{64, 32}, {16, 64}, {64, 32}, {64, 64}, {16, 64}};
+        size_t src = 0, dst = 0;
+        for (int w = 0; w < 5; ++w) {
+            const int N = shp[w][0], K = shp[w][1];
+            for (int n = 0; n < N; ++n)
+                for (int k = 0; k < K; ++k) {
+                    const size_t off = (size_t)(n >> 3) * (K / 8) * 128 + (size_t)(k >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2;
+                    blob[dst + off / 2] = hp[src + (size_t)n * K + k];
+                }
+            src += (size_t)N * K;
+            dst += (size_t)N * K;
+        }
+        D2R_CUDA(cudaMalloc(&m->w_umma_dev, 20480));
+        D2R_CUDA(cudaMemcpy(m->w_umma_dev, blob.data(), 20480, cudaMemcpyHostToDevice));
+        d.w_umma = (const unsigned char*)m->w_umma_dev;
+    }
     const __half* p = (const __half*)m->params_dev;
     d.w_d0 = p; p += 64 * 32;
     d.w_d1 = p; p += 16 * 64;
@@ -342,19 +375,30 @@ extern "C" int d2r_model_load(const void* params_f16_host, size_t n_params, cons
         for (int a = 0; a < 3; ++a) d.occ_ctr[a] = (float)ctr[a];
         d.occ_r2 = lo[0] <= hi[0] ? (float)(rad * rad) : -1.0f;     // nothing occupied: no sphere
     }
-    cudaFree(grid_dev);
-    cudaFree(mean_dev);
     D2R_CUDA(cudaDeviceSynchronize());
+    return D2R_OK;
+}
+
+extern "C" int d2r_model_load(const void* params_f16_host, size_t n_params, const float* density_grid_f32_host,
+                              size_t n_grid_cells, const d2r_model_cfg* cfg, int device, d2r_model** out) {
+    D2R_REQUIRE(params_f16_host && density_grid_f32_host && cfg && out, "d2r_model_load: null argument");
+    DeviceGuard dg(device);
+    d2r_model* m = new d2r_model();
+    memset(m, 0, sizeof(*m));
+    m->device = device;
+    const int rc = model_load_impl(params_f16_host, n_params, density_grid_f32_host, n_grid_cells, cfg, device, m);
+    if (rc != D2R_OK) { d2r_model_free(m); return rc; }
     *out = m;
     return D2R_OK;
 }
 
 extern "C" void d2r_model_free(d2r_model* m) {
     if (!m) return;
-    cudaSetDevice(m->device);
+    DeviceGuard dg(m->device);
     cudaFree(m->params_dev);
     cudaFree(m->bitfield_dev);
     cudaFree(m->bitfield_lin_dev);
+    cudaFree(m->w_umma_dev);
     delete m;
 }
 
@@ -369,7 +413,7 @@ extern "C" int d2r_model_set_min_transmittance(d2r_model* m, float v) {
 extern "C" int d2r_model_get_bitfield(const d2r_model* m, uint8_t* out, size_t n_bytes) {
     D2R_REQUIRE(m && out, "d2r_model_get_bitfield: null argument");
     D2R_REQUIRE(n_bytes == (size_t)NERF_GRID_N_CELLS / 8 * NERF_CASCADES, "d2r_model_get_bitfield: size must be 8*128^3/8");
-    D2R_CUDA(cudaSetDevice(m->device));
+    DeviceGuard dg(m->device);
     D2R_CUDA(cudaMemcpy(out, m->bitfield_dev, n_bytes, cudaMemcpyDeviceToHost));
     return D2R_OK;
 }
@@ -384,34 +428,45 @@ extern "C" int d2r_view_prepare(const d2r_camera* cam, int device, d2r_view** ou
     D2R_REQUIRE(cam && out, "d2r_view_prepare: null argument");
     D2R_REQUIRE(cam->width > 0 && cam->height > 0 && cam->width <= 16384 && cam->height <= 16384, "d2r_view_prepare: bad resolution");
     D2R_REQUIRE(cam->lens_mode == 0 || cam->lens_mode == 1, "d2r_view_prepare: only perspective and OpenCV lenses are on this path");
-    D2R_CUDA(cudaSetDevice(device));
+    DeviceGuard dg(device);
     d2r_view* v = new d2r_view();
+    memset(v, 0, sizeof(*v));
     v->device = device;
     v->W = cam->width;
     v->H = cam->height;
     v->cam = *cam;
-    D2R_CUDA(cudaMalloc(&v->dirs_dev, (size_t)v->W * v->H * sizeof(float2)));
+    if (cudaMalloc(&v->dirs_dev, (size_t)v->W * v->H * sizeof(float2)) != cudaSuccess) { delete v; set_error("d2r_view_prepare: cudaMalloc failed"); return D2R_ERR_NOMEM; }
     dim3 threads(16, 8), blocks((v->W + 15) / 16, (v->H + 7) / 8);
     k_view_dirs<<<blocks, threads>>>(v->W, v->H, cam->focal[0], cam->focal[1], cam->screen_center[0], cam->screen_center[1],
                                      cam->lens_mode, cam->lens_params[0], cam->lens_params[1], cam->lens_params[2],
                                      cam->lens_params[3], v->dirs_dev);
     count_launch();
-    D2R_CUDA(cudaGetLastError());
-    D2R_CUDA(cudaDeviceSynchronize());
+    {
+        const int W = v->W, H = v->H;
+        DevBuf rb;
+        if (cudaMalloc(&rb.p, (size_t)2 * (W + H) * sizeof(float)) != cudaSuccess) { d2r_view_free(v); set_error("d2r_view_prepare: cudaMalloc failed"); return D2R_ERR_NOMEM; }
+        float* r = (float*)rb.p;
+        k_view_ranges<<<(std::max(W, H) + 127) / 128, 128>>>(W, H, v->dirs_dev, r, r + W, r + 2 * W, r + 2 * W + H);
+        count_launch();
+        v->ranges_host = new float[(size_t)2 * (W + H)];
+        const cudaError_t e = cudaMemcpy(v->ranges_host, r, (size_t)2 * (W + H) * sizeof(float), cudaMemcpyDeviceToHost);   // also the sync of this set-up call
+        if (e != cudaSuccess) { d2r_view_free(v); set_error(std::string("d2r_view_prepare: ") + cudaGetErrorString(e)); return D2R_ERR_CUDA; }
+    }
     *out = v;
     return D2R_OK;
 }
 
 extern "C" void d2r_view_free(d2r_view* v) {
     if (!v) return;
-    cudaSetDevice(v->device);
+    DeviceGuard dg(v->device);
     cudaFree(v->dirs_dev);
+    delete[] v->ranges_host;
     delete v;
 }
 
 extern "C" int d2r_view_get_dirs(const d2r_view* v, float* out) {
     D2R_REQUIRE(v && out, "d2r_view_get_dirs: null argument");
-    D2R_CUDA(cudaSetDevice(v->device));
+    DeviceGuard dg(v->device);
     D2R_CUDA(cudaMemcpy(out, v->dirs_dev, (size_t)v->W * v->H * sizeof(float2), cudaMemcpyDeviceToHost));
     return D2R_OK;
 }

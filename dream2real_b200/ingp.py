@@ -219,6 +219,15 @@ def decode_snapshot(cfg: Dict[str, Any]) -> Snapshot:
         if n.get("otype") != "FullyFusedMLP" or int(n.get("n_neurons", 128)) != 64 \
            or n.get("activation", "ReLU") != "ReLU" or n.get("output_activation", "None") != "None":
             raise SnapshotError("this path supports FullyFusedMLP(64, ReLU, None) networks only")
+    # what the kernels hard-code beyond the shapes: SH degree 4 on the 3 direction dims and no extra learnable dims (they
+    # would widen the rgb-network input, nerf_network.h:105-140).  The density / rgb activations are not part of a snapshot
+    # (runtime state, testbed.h:745-746 and testbed_nerf.cu:2145): the path's Exponential / Logistic always apply.
+    denc = cfg.get("dir_encoding", {})
+    sh = denc["nested"][0] if denc.get("otype") == "Composite" and denc.get("nested") else denc
+    if sh.get("otype") != "SphericalHarmonics" or int(sh.get("degree", 4)) != 4:
+        raise SnapshotError("this path supports the SphericalHarmonics(degree 4) direction encoding only")
+    if int(ds.get("n_extra_learnable_dims", 0)) != 0:
+        raise SnapshotError("n_extra_learnable_dims != 0 is not on this path")
     d_shapes = mlp_shapes(L * F, 64, int(net["n_hidden_layers"]), 16)
     c_shapes = mlp_shapes(32, 64, int(rgbnet["n_hidden_layers"]), 16)
     if len(d_shapes) != 2 or len(c_shapes) != 3:

@@ -54,8 +54,8 @@ class renderer:
         self.out_render_path = os.path.join(self.root, "cb_render")
         os.makedirs(self.out_render_path, exist_ok=True)
         self.last_n_samples = 0
-        self.last_rects = None        # int32 CUDA [K,4] / uint8 CUDA [H,W,3] of the last single-view render(): outside its
-        self.last_bg_u8 = None        # rectangle a frame equals the composited background (clip_scoring exploits it)
+        self.last_rects = None        # int32 CUDA [K,4] / uint8 CUDA [H,W,3] of the last single-view render(return_tensor=True):
+        self.last_bg_u8 = None        # outside its rectangle a frame equals the composited background (preprocessing exploits it)
         self.count_samples = False    # True: read the network-sample count back after every launch (one host sync each)
 
     # ---- background -----------------------------------------------------------------------------
@@ -82,24 +82,31 @@ class renderer:
         return bg_image, bg_depth
 
     # ---- the hot loop ---------------------------------------------------------------------------
-    def render(self, valid_poses, render_poses, render_cam_pose_idx, depths_gt=None, movable_masks=None, save=True,
-               return_tensor=False):
-        """valid_poses [K,4,4] (NeRF convention), render_poses [L,4,4], render_cam_pose_idx list[int],
-        depths_gt torch [L,Hs,Ws], movable_masks torch bool [n_views,Hs,Ws].
-        Returns the reference's list of K*L uint8 [H,W,3] arrays, or (return_tensor=True) one uint8
-        CUDA tensor [K*L,H,W,3] that never leaves the device."""
+    def iter_render(self, valid_poses, render_poses, render_cam_pose_idx, depths_gt=None, movable_masks=None, save=False,
+                    chunk=None, out=None):
+        """The streaming form of render(): yields (render_idx, lo, hi, frames, rects, bg_u8) per launch of at most `chunk`
+        candidates -- frames uint8 CUDA [hi-lo,H,W,3] (a reused buffer unless `out` [K*L,H,W,3] is given: consume it, on the
+        current stream, before asking for the next chunk), rects int32 CUDA [hi-lo,4] and bg_u8 uint8 CUDA [H,W,3]: outside
+        its rectangle a frame equals bg_u8 (ClipVision.preprocess exploits it).  Only O(chunk) frames exist at any time, so
+        the reference's full pose grids (70 000 poses for the shopping demo, configs/shopping_demo.json:28) stream through
+        a few GB.  save=True streams the PNGs of combined_rendering.py:157-159 chunk by chunk."""
         import torch
         T_WO_1 = accio2ngp.converter(np.expand_dims(self.fg_obj.pose.cpu().numpy(), axis=0)).astype(np.float64)[0]
         valid_poses = np.asarray(valid_poses, dtype=np.float64).reshape(-1, 4, 4)
+        K = len(valid_poses)
         W, H = self.resolution
+        chunk = int(chunk) if chunk else self.max_candidates_per_launch
+        save = save and len(render_cam_pose_idx) == 1
         if save:
             if os.path.exists(self.out_render_path):
                 shutil.rmtree(self.out_render_path)
             os.makedirs(self.out_render_path)
-        outs = []
         self.last_n_samples = 0
         fg = self.fg_obj.vis_model
         inv_T_WO_2 = np.linalg.inv(valid_poses)                                   # [K,4,4]
+        dev = torch.device("cuda", fg.device)
+        buf = None if out is not None else torch.empty((min(chunk, K), H, W, 3), dtype=torch.uint8, device=dev)
+        rect_buf = torch.empty((min(chunk, K), 4), dtype=torch.int32, device=dev) if out is None else None
         for render_idx in range(len(render_cam_pose_idx)):
             view_idx = render_cam_pose_idx[render_idx]
             T_WC_1 = np.asarray(render_poses[render_idx], dtype=np.float64)
@@ -111,26 +118,43 @@ class renderer:
             fg.render_ground_truth = False
             # T_WC_2 = T_WO_1 . (T_WO_2^-1 . T_WO_1) . (T_WO_1^-1 . T_WC_1), same association as the reference
             cams = T_WO_1 @ (inv_T_WO_2 @ T_WO_1) @ (np.linalg.inv(T_WO_1) @ T_WC_1)
-            out = torch.empty((len(valid_poses), H, W, 3), dtype=torch.uint8, device=bg_image.device)
-            rects = torch.empty((len(valid_poses), 4), dtype=torch.int32, device=bg_image.device)
-            bg_u8 = torch.empty((H, W, 3), dtype=torch.uint8, device=bg_image.device)
-            for s in range(0, len(valid_poses), self.max_candidates_per_launch):
-                e = min(s + self.max_candidates_per_launch, len(valid_poses))
-                fg.render_composite_batch(cams[s:e, :3, :], W, H, bg_image, bg_depth, out_u8=out[s:e], count_samples=self.count_samples,
-                                          rects_out=rects[s:e], bg_u8_out=bg_u8 if s == 0 else None)
+            bg_u8 = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+            rects_all = torch.empty((K, 4), dtype=torch.int32, device=dev) if out is not None else None
+            for s in range(0, K, chunk):
+                e = min(s + chunk, K)
+                frames = out[render_idx * K + s: render_idx * K + e] if out is not None else buf[: e - s]
+                rects = rects_all[s:e] if out is not None else rect_buf[: e - s]
+                fg.render_composite_batch(cams[s:e, :3, :], W, H, bg_image, bg_depth, out_u8=frames, count_samples=self.count_samples,
+                                          rects_out=rects, bg_u8_out=bg_u8 if s == 0 else None)
                 if self.count_samples:
                     self.last_n_samples += fg.last_n_samples
-            outs.append(out)
-            self.last_rects, self.last_bg_u8 = (rects, bg_u8) if len(render_cam_pose_idx) == 1 else (None, None)
-        renders = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
-        if save and len(render_cam_pose_idx) == 1:
-            import cv2
-            host = renders.cpu().numpy()
-            for i in range(host.shape[0]):
-                cv2.imwrite(os.path.join(self.out_render_path, f"cb_rgb_{i:04d}.png"), cv2.cvtColor(host[i], cv2.COLOR_RGB2BGR))
+                if save:
+                    import cv2
+                    host = frames.cpu().numpy()
+                    for i in range(host.shape[0]):
+                        cv2.imwrite(os.path.join(self.out_render_path, f"cb_rgb_{s + i:04d}.png"), cv2.cvtColor(host[i], cv2.COLOR_RGB2BGR))
+                yield render_idx, s, e, frames, rects, bg_u8
+            self.last_rects, self.last_bg_u8 = (rects_all, bg_u8) if (out is not None and len(render_cam_pose_idx) == 1) else (None, None)
+
+    def render(self, valid_poses, render_poses, render_cam_pose_idx, depths_gt=None, movable_masks=None, save=True,
+               return_tensor=False):
+        """valid_poses [K,4,4] (NeRF convention), render_poses [L,4,4], render_cam_pose_idx list[int],
+        depths_gt torch [L,Hs,Ws], movable_masks torch bool [n_views,Hs,Ws].
+        Returns the reference's list of K*L uint8 [H,W,3] arrays (combined_rendering.py:73-163), or (return_tensor=True) one
+        uint8 CUDA tensor [K*L,H,W,3] that never leaves the device.  Both materialise every frame, like the reference;
+        optimise_pose_grid streams through iter_render instead."""
+        import torch
+        K = int(np.asarray(valid_poses).reshape(-1, 4, 4).shape[0])
+        W, H = self.resolution
+        L = len(render_cam_pose_idx)
         if return_tensor:
-            return renders
-        host = renders.cpu().numpy()
+            out = torch.empty((K * L, H, W, 3), dtype=torch.uint8, device=torch.device("cuda", self.fg_obj.vis_model.device))
+            for _ in self.iter_render(valid_poses, render_poses, render_cam_pose_idx, depths_gt, movable_masks, save=save, out=out):
+                pass
+            return out
+        host = np.empty((K * L, H, W, 3), np.uint8)
+        for render_idx, s, e, frames, _, _ in self.iter_render(valid_poses, render_poses, render_cam_pose_idx, depths_gt, movable_masks, save=save):
+            host[render_idx * K + s: render_idx * K + e] = frames.cpu().numpy()
         return [host[i] for i in range(host.shape[0])]
 
     # ---- sensor depth / mask rectification (combined_rendering.py:166-209) -------------------------

@@ -98,6 +98,9 @@ class Testbed:
         self.mode = TestbedMode.Nerf
         self.background_color = [float(c) for c in snap.background_color]      # testbed.cu:4823
         self.exposure = snap.exposure
+        if float(snap.exposure) != 0.0:
+            # tonemap_kernel scales by 2^exposure (render_buffer.cu:529-561); Dream2Real snapshots are saved with exposure 0
+            raise RuntimeError(f"snapshot exposure {snap.exposure} != 0 is not on the Dream2Real path")
         self.nerf.cone_angle_constant = snap.cone_angle_constant
         self._camera_ngp = snap.snapshot_camera.astype(np.float32)
         if snap.density_grid.size == 0:
@@ -154,8 +157,17 @@ class Testbed:
         """Testbed::render_to_cpu (python_api.cu:123-201) -> float32 [h,w,4] linear premultiplied."""
         if spp != 1 or not linear:
             raise RuntimeError("only spp=1, linear=True renders are on the Dream2Real path")
-        if self.render_mode not in (RenderMode.Shade, RenderMode.Depth):
+        if self.render_mode not in (RenderMode.Shade, RenderMode.Depth, RenderMode.Cost):
             raise RuntimeError(f"render_mode {self.render_mode} is not on the Dream2Real path")
+        if self.render_mode == RenderMode.Cost:
+            # shade_kernel_nerf (testbed_nerf.cu:1322-1326): rgb = n_steps / 128, alpha 1 on the rays it keeps; the rest of
+            # the frame is the tonemap background blend
+            rgba, _, cost = self.render_batch(self._camera_ngp[None], width, height, ngp_convention=True, want_shade=True,
+                                              want_depth=False, want_cost=True)
+            out, n = rgba[0].cpu().numpy(), cost[0].cpu().numpy()
+            kept = n > 0
+            out[kept] = np.stack([n[kept] / 128.0] * 3 + [np.ones_like(n[kept])], -1)
+            return out
         rgba, depth = self.render_batch(self._camera_ngp[None], width, height, ngp_convention=True,
                                         want_shade=self.render_mode == RenderMode.Shade,
                                         want_depth=self.render_mode == RenderMode.Depth)
@@ -201,9 +213,10 @@ class Testbed:
                                                        s.dataset_offset, s.from_mitsuba), dtype=np.float32)
 
     def render_batch(self, cams, width: int, height: int, ngp_convention: bool = False, want_shade: bool = True,
-                     want_depth: bool = True, count_samples: bool = False):
+                     want_depth: bool = True, count_samples: bool = False, want_cost: bool = False):
         """K renders in one launch.  cams: [K,3|4,4] NeRF convention (or NGP if ngp_convention).
-        Returns torch float32 CUDA tensors ([K,H,W,4] shade or None, [K,H,W,4] depth or None)."""
+        Returns torch float32 CUDA tensors ([K,H,W,4] shade or None, [K,H,W,4] depth or None) and, with want_cost, a
+        third one: [K,H,W] step counts (the reference's Cost render mode before the /128)."""
         import torch
         self._require()
         self._sync_min_T()
@@ -214,14 +227,16 @@ class Testbed:
         dev = torch.device("cuda", self.device)
         shade = torch.empty((K, height, width, 4), dtype=torch.float32, device=dev) if want_shade else None
         depth = torch.empty((K, height, width, 4), dtype=torch.float32, device=dev) if want_depth else None
+        cost = torch.empty((K, height, width), dtype=torch.float32, device=dev) if want_cost else None
         ns = torch.zeros(1, dtype=torch.int64, device=dev) if count_samples else None
         with torch.cuda.device(dev):
-            N.check(N.lib().d2r_render(self._model, view, cams_ngp.ctypes.data, K, N.f4(self.background_color),
-                                       shade.data_ptr() if want_shade else None, depth.data_ptr() if want_depth else None,
-                                       ns.data_ptr() if count_samples else None, N.stream_ptr()), "render")
+            N.check(N.lib().d2r_render_ex(self._model, view, cams_ngp.ctypes.data, K, N.f4(self.background_color),
+                                          shade.data_ptr() if want_shade else None, depth.data_ptr() if want_depth else None,
+                                          cost.data_ptr() if want_cost else None,
+                                          ns.data_ptr() if count_samples else None, N.stream_ptr()), "render")
         if count_samples:
             self.last_n_samples = int(ns.item())
-        return shade, depth
+        return (shade, depth, cost) if want_cost else (shade, depth)
 
     def render_composite_batch(self, cams, width: int, height: int, bg_rgba, bg_depth, out_u8=None,
                                ngp_convention: bool = False, count_samples: bool = False, rects_out=None, bg_u8_out=None):

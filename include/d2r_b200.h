@@ -14,10 +14,16 @@
  *     available through d2r_last_error() (thread-local).  No C++ exception crosses the boundary.
  *   - plain pointers and sizes only.  Pointers named *_dev are DEVICE pointers owned by the
  *     caller (typically torch tensors); pointers named *_host are host pointers.
- *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous w.r.t. the host unless
- *     stated otherwise and never synchronise behind the caller's back (the *_host convenience
- *     entry points do synchronise: they return host results).
- *   - handles are not re-entrant; different handles / devices may be used concurrently.
+ *   - `stream` is a cudaStream_t passed as void*.  The per-candidate calls (d2r_render*, d2r_clip_*,
+ *     d2r_score) only enqueue work: they never wait for the device.  The candidate cameras are a HOST
+ *     array (the pose grid is built on the host): the library plans every candidate's screen rectangle
+ *     from it on the CPU and uploads cameras + plan with one pinned asynchronous copy, so no launch
+ *     needs a read-back.  Exceptions, all outside the steady state: a call whose scratch must grow
+ *     (first launch of a size class) goes through cudaMalloc/cudaFree; a host that runs more than 8
+ *     launches ahead of the device waits for the oldest upload slot; the set-up calls
+ *     (d2r_model_load, d2r_view_prepare, d2r_clip_load) and the *_get_* read-backs synchronise.
+ *   - handles are not re-entrant; different handles / streams / devices may be used concurrently
+ *     (launch scratch is kept per stream).  The caller's current device is never left changed.
  */
 #ifndef D2R_B200_H
 #define D2R_B200_H
@@ -103,6 +109,13 @@ int d2r_render(const d2r_model* m, const d2r_view* v, const float* cams_ngp_host
                const float background_rgba[4], float* rgba_out_dev, float* depth_out_dev,
                unsigned long long* n_samples_out_dev, void* stream);
 
+/* d2r_render plus the reference's Cost render mode (testbed_nerf.cu:1322-1326: payload.n_steps): cost_out_dev [K,H,W]
+ * float32 = the step count of every ray the reference keeps (final alpha > 0.001), 0 elsewhere; NULL = skip.
+ * The parity tests use it to tell single-sample flips at occupancy-cell boundaries from arithmetic differences. */
+int d2r_render_ex(const d2r_model* m, const d2r_view* v, const float* cams_ngp_host, int K,
+                  const float background_rgba[4], float* rgba_out_dev, float* depth_out_dev,
+                  float* cost_out_dev, unsigned long long* n_samples_out_dev, void* stream);
+
 /* Fused candidate render + depth-test composite + colour post-process =
  * reconstruction/combined_rendering.py:117-155 for K candidate poses of the movable object:
  *   fg Shade + fg Depth (one march), fg_d<0.05 -> 100, bg_d<0.05 -> 100, fg where fg_d < bg_d,
@@ -185,6 +198,11 @@ int d2r_gemm_f16(const void* a_dev, int lda, const void* b_dev, int ldb, int M, 
 int d2r_profile_enable(int device, int on);   /* also resets the accumulated state */
 int d2r_profile_read(int device, float* march_ms_total, int* n_launches,
                      unsigned long long* n_samples, unsigned long long* n_tiles);
+/* The raw counters of the profiled launches (synchronises): [0] samples, [1] rays, then the role statistics of k_march_ws
+ * in SM cycles summed over warps -- [2] gather total, [3] gather waiting for its MLP round, [4] occupancy walk, [5] hash-grid
+ * gather, [6] slot refill, [7] epilogue total, [8] epilogue waiting for an MMA, [9] epilogue items, [10] MMA thread total,
+ * [11] MMA thread issuing, [12] gather rounds.  tools/ws_stats.py prints them.                                          */
+int d2r_profile_read_stats(int device, unsigned long long* out16_host);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char* d2r_last_error(void);

@@ -1,0 +1,159 @@
+"""-m gpu: parity AT THE BENCHMARKED CONFIGURATION -- 800x800 (and the reference's 336x336), 2^19-entry hash tables, the
+synthetic bench scenes, the default march kernel -- against
+  (a) the REAL reference renderer: pyngp renders of the very same .ingp files (tests/golden/synth_<scene>.npz, made on a
+      B200 by tests/golden/make_golden_synth.py; the scenes are rebuilt here from the same seed), and
+  (b) the numpy oracle on the same inputs.
+North-star tolerance: 1e-3 max pixel error on the float renders.  The two renderers differ in arithmetic the spec allows
+(fp16-accumulating wmma + --use_fast_math there, fp32-accumulating tcgen05 here), which moves a sample across an occupancy
+cell boundary now and then; the Cost render mode (per-ray step count) tells exactly those rays apart: every value above
+1e-3 must sit on a ray whose step count differs from the reference's, and their number is bounded and reported."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SCENES = ["shopping", "pool_triangle", "shelf"]
+
+
+@pytest.fixture(scope="module")
+def worlds(tmp_path_factory):
+    """scene name -> (scene dict, task model, dir), built once per module (2^19 tables: a few seconds each)"""
+    import torch
+    from dream2real_b200 import synth
+    out = {}
+
+    def get(name):
+        if name not in out:
+            d = str(tmp_path_factory.mktemp(f"bench_{name}"))
+            scene = synth.make_scene(name, d, log2_hashmap_size=19, seed=1234)
+            out[name] = (scene, synth.SyntheticTaskModel(scene, "g", None, torch.device("cuda")), d)
+        return out[name]
+    return get
+
+
+def _crop(a, rect):
+    y0, y1, x0, x1 = [int(v) for v in rect]
+    return a[y0:y1, x0:x1]
+
+
+@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("res", [336, 800])
+def test_fg_render_matches_pyngp(worlds, golden_dir, name, res):
+    """fg Shade / Depth / Cost of the candidates' virtual cameras vs pyngp (combined_rendering.py:117-130)."""
+    g = np.load(os.path.join(golden_dir, f"synth_{name}.npz"))
+    scene, tm, d = worlds(name)
+    fg = tm.movable_obj.vis_model
+    fg.set_camera_to_training_view(0)
+    fg.background_color = [0.0, 0.0, 0.0, 0.0]
+    n = sum(1 for k in g.files if k.startswith(f"shade_{res}_"))
+    shade, depth, cost = fg.render_batch(g["cams"][:n], res, res, want_cost=True)
+    shade, depth, cost = shade.cpu().numpy(), depth.cpu().numpy(), cost.cpu().numpy()
+    tot_bad = tot_unexplained = tot = 0
+    for i in range(n):
+        rect = g[f"rect_{res}_{i}"]
+        # nothing outside the golden crop (the crop holds every pixel pyngp touched, plus a margin)
+        outside = np.ones((res, res), bool)
+        outside[int(rect[0]):int(rect[1]), int(rect[2]):int(rect[3])] = False
+        assert not shade[i][outside].any() and not depth[i][outside].any() and not cost[i][outside].any()
+        s, dp, c = _crop(shade[i], rect), _crop(depth[i], rect), _crop(cost[i], rect)
+        e = np.abs(s - g[f"shade_{res}_{i}"]).max(-1)
+        ed = np.abs(dp[..., 0] - g[f"depth_{res}_{i}"])
+        same_steps = c == g[f"cost_{res}_{i}"]
+        bad = e > 1e-3
+        unexplained = bad & same_steps
+        tot += e.size
+        tot_bad += int(bad.sum())
+        tot_unexplained += int(unexplained.sum())
+        steps_ref = float(g[f"cost_{res}_{i}"].sum())
+        print(f"{name} {res} cand {i}: shade max {e.max():.5f} mean {e.mean():.2e}; >1e-3: {int(bad.sum())} of {e.size} px "
+              f"({int(unexplained.sum())} with the reference's step count, max {e[same_steps].max():.5f}); depth max {ed.max():.5f} "
+              f"(same steps {ed[same_steps].max():.5f}); steps {c.sum():.0f} vs {steps_ref:.0f}; rays with another step count {int((~same_steps).sum())}")
+        # rays that took the reference's samples: north-star tolerance, max error
+        assert e[same_steps].max() < 1e-3
+        assert ed[same_steps].max() < 1e-3 * max(1.0, float(g[f"depth_{res}_{i}"].max()))
+        # rays with a different step count (a sample flipped across a cell boundary): few, and bounded
+        assert (~same_steps).mean() < 0.02 and e.max() < 3e-2
+        assert abs(c.sum() - steps_ref) / steps_ref < 2e-3
+        assert np.abs(dp[..., 3] - g[f"depth_a_{res}_{i}"])[same_steps].max() < 1e-3
+    print(f"{name} {res}: values above 1e-3: {tot_bad} of {tot} pixels, {tot_unexplained} unexplained by a step-count difference")
+    assert tot_unexplained == 0
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_composited_frames_match_pyngp_pipeline(worlds, golden_dir, name):
+    """renderer.render (background once, fused candidate render + depth-test composite) vs the reference pipeline run with
+    pyngp + NumPy (combined_rendering.py:95-155): u8 frames inside the candidates' footprint, and the background render."""
+    from dream2real_b200.reconstruction.combined_rendering import renderer
+    from dream2real_b200.utils import accio2ngp
+    g = np.load(os.path.join(golden_dir, f"synth_{name}.npz"))
+    scene, tm, d = worlds(name)
+    for res in (336, 800):
+        n = sum(1 for k in g.files if k.startswith(f"u8_{res}_") and not k.startswith("u8_bg"))
+        r = renderer(d, tm, resolution=res)
+        rp = accio2ngp.converter(scene["opt_cam_poses"][:1])
+        assert np.allclose(rp[0], g["render_pose"])
+        bg_image, _ = r.render_background(rp[0], 0, tm.depths[0], tm.movable_masks[0])
+        bg = bg_image.cpu().numpy()
+        eb = np.abs(bg[::8, ::8] - g[f"bg_strided_{res}"]).max(-1)
+        w0 = [int(v) for v in g[f"bg_window_origin_{res}"]]
+        win = g[f"bg_window_{res}"]
+        ew = np.abs(bg[w0[0]:w0[0] + win.shape[0], w0[1]:w0[1] + win.shape[1]] - win).max(-1)
+        print(f"{name} {res} bg: strided max {eb.max():.5f} p99.9 {np.percentile(eb, 99.9):.5f} >1e-3 {int((eb > 1e-3).sum())}/{eb.size}; "
+              f"window max {ew.max():.5f} >1e-3 {int((ew > 1e-3).sum())}/{ew.size}")
+        assert np.percentile(eb, 99.9) < 1e-3 and np.percentile(ew, 99.9) < 1e-3 and (eb > 1e-3).mean() < 2e-3 and (ew > 1e-3).mean() < 2e-3
+        frames = r.render(accio2ngp.converter(g["poses"][:n]), rp, [0], tm.depths[:1], tm.movable_masks, save=False, return_tensor=True).cpu().numpy()
+        for i in range(n):
+            got = _crop(frames[i], g[f"rect_{res}_{i}"]).astype(int)
+            diff = np.abs(got - g[f"u8_{res}_{i}"].astype(int)).max(-1)
+            print(f"{name} {res} cand {i}: u8 diff >1 LSB {float((diff > 1).mean()):.5f} max {diff.max()}")
+            assert (diff > 1).mean() < 5e-3
+
+
+def test_bench_scene_matches_oracle_at_800(worlds):
+    """The bench configuration itself (shopping, 800x800, 2^19 tables, default kernel) vs the numpy oracle on the same
+    inputs: float Shade/Depth of two candidates and the composited u8 frames."""
+    import torch
+    from dream2real_b200 import ingp
+    from dream2real_b200.reconstruction.combined_rendering import renderer
+    from dream2real_b200.utils import accio2ngp
+    from oracle import ngp_oracle as O
+    from oracle import post_oracle as PO
+    scene, tm, d = worlds("shopping")
+    res = 800
+    grid = PO.sample_poses_grid(scene["scene_centre"], [64, 64, 1, 1, 1, 1], scene["scene_type"]).reshape(-1, 4, 4).numpy().astype(np.float64)
+    poses = grid[[1234, 2900]]
+    fgs = ingp.load_snapshot(os.path.join(d, "fg_base.ingp"))
+    bits, _ = O.build_bitfield(fgs.density_grid, fgs.max_cascade)
+    vs = O.view_setup(fgs, 0, res, res)
+    dirs = O.camera_plane_dirs(vs)
+    box = O.occupied_box(bits, fgs.max_cascade)
+    rp = PO.converter(scene["opt_cam_poses"][:1])
+    vp = PO.converter(poses)
+    T1 = PO.converter(scene["fg_pose"][None])[0]
+    cams = np.stack([PO.convert_virtual_pose(T1, vp[i], rp[0]) for i in range(len(poses))])
+    fg = tm.movable_obj.vis_model
+    fg.set_camera_to_training_view(0)
+    fg.background_color = [0.0, 0.0, 0.0, 0.0]
+    shade, depth = fg.render_batch(cams, res, res)
+    r = renderer(d, tm, resolution=res)
+    frames = r.render(accio2ngp.converter(poses), accio2ngp.converter(scene["opt_cam_poses"][:1]), [0], tm.depths[:1], tm.movable_masks,
+                      save=False, return_tensor=True).cpu().numpy()
+    bg_image, bg_depth = r.render_background(rp[0], 0, tm.depths[0], tm.movable_masks[0])
+    bg_image, bg_depth = bg_image.cpu().numpy(), bg_depth.cpu().numpy()
+    for i in range(len(poses)):
+        so, do = O.render(fgs, bits, vs, cams[i][:3], both=True, background_color=[0, 0, 0, 0], plane_dirs=dirs, cull_box=box)
+        e = np.abs(shade[i].cpu().numpy() - so).max(-1)
+        ed = np.abs(depth[i].cpu().numpy()[..., 0] - do[..., 0])
+        hit = so[..., 3] > 0
+        print(f"oracle 800 cand {i}: hit px {int(hit.sum())}, shade max {e.max():.5f} p99.9(hit) {np.percentile(e[hit], 99.9):.5f} >1e-3 {int((e > 1e-3).sum())}; "
+              f"depth max {ed.max():.5f} >1e-3 {int((ed > 1e-3).sum())}")
+        assert hit.sum() > 2000
+        assert np.percentile(e[hit], 99.9) < 1e-3 and (e > 1e-3).sum() < 0.005 * hit.sum() and e.max() < 3e-2
+        assert np.percentile(ed[hit], 99.9) < 1e-3
+        ref = PO.composite(bg_image, bg_depth, so, do[..., 0])
+        diff = np.abs(frames[i].astype(int) - ref.astype(int)).max(-1)
+        print(f"oracle 800 cand {i}: u8 diff >1 LSB {int((diff > 1).sum())} px, max {diff.max()}")
+        assert (diff > 1).sum() < 0.005 * hit.sum()
+        assert (diff > 0)[~hit].sum() == 0      # outside the object's footprint: exactly the composited background

@@ -85,8 +85,8 @@ def test_second_view_and_multi_view_order(tmp_path):
 
 
 def test_candidates_are_independent_at_full_resolution(tmp_path):
-    """Size-independent properties at the bench resolution (800x800, 2^19-entry tables): any chunking of a batch gives
-    bit-identical frames; the initial pose reproduces the plain composite of an un-moved object; an object moved out
+    """Size-independent properties at the bench resolution (800x800, 2^19-entry tables): any chunking of a batch (different
+    occupancy of the persistent kernel's ray slots, different hit-list order) gives bit-identical frames; the initial pose reproduces the plain composite of an un-moved object; an object moved out
     of the frame leaves exactly the background."""
     import torch
     from dream2real_b200 import synth
@@ -147,7 +147,7 @@ def test_delta_preprocessing_is_bit_identical(tmp_path, res, rot90):
                       save=False, return_tensor=True)
     rects = r.last_rects.cpu().numpy()
     print("rects", rects.tolist())
-    assert (rects[:, 2] < rects[:, 0]).any() or True
+    assert (rects[-2, 2] < rects[-2, 0]) and tuple(rects[-1]) == (0, 0, res - 1, res - 1)      # the empty and the full-frame rectangle
     hf = make_hf_clip("ViT-B/32", seed=3)
     cv = ClipVision(hf, max_batch=16)
     full, _ = cv.preprocess(frames, rot90=rot90)
@@ -194,14 +194,49 @@ def test_multi_view_scoring_is_the_mean_over_views(tmp_path):
     assert torch.allclose(mx, torch.maximum(per_view[0], per_view[1]), rtol=1e-5, atol=1e-6)
 
 
-def test_round_kernels_forced_on_small_renders():
-    """Small launches take the fused kernel by default; D2R_MARCH=split forces k_gather_round / k_mlp_round on them too.
-    The mode is read once per process, so the golden-render parity tests run again in a child process."""
+def _frame_hashes(d, res=800, n=43):
+    """per-candidate sha1 of the composited u8 frames of n shopping candidates (2^19 tables)"""
+    import hashlib
+
+    import torch
+    from dream2real_b200 import synth
+    from dream2real_b200.reconstruction.combined_rendering import renderer
+    from dream2real_b200.utils import accio2ngp
+    scene = synth.make_scene("shopping", d, log2_hashmap_size=19, seed=1234)
+    tm = synth.SyntheticTaskModel(scene, "g", None, torch.device("cuda"))
+    poses = _grid_poses(scene, [64, 64, 1, 1, 1, 1], list(range(0, 4096, 4096 // n))[:n])
+    r = renderer(d, tm, resolution=res, max_candidates_per_launch=16)
+    frames = r.render(accio2ngp.converter(poses), accio2ngp.converter(scene["opt_cam_poses"][:1]), [0], tm.depths[:1], tm.movable_masks,
+                      save=False, return_tensor=True).cpu().numpy()
+    return [hashlib.sha1(f.tobytes()).hexdigest() for f in frames]
+
+
+def test_split_kernels_give_identical_frames(tmp_path):
+    """The A/B partner of the default kernel (D2R_MARCH=split: k_gather_round / k_mlp_round, the round-1 path) runs the same
+    arithmetic per sample: bit-identical frames at the bench configuration, and green golden-render parity on its own.
+    The mode is read once per process, so the split side runs in a child process."""
+    import json
     import os
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
+    mine = _frame_hashes(str(tmp_path / "a"))
     env = dict(os.environ, D2R_MARCH="split")
+    out = str(tmp_path / "split.json")
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "hashes", str(tmp_path / "b"), out], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    theirs = json.load(open(out))
+    assert len(mine) == len(theirs) and len(set(mine)) > 1
+    assert mine == theirs, [i for i, (a, b) in enumerate(zip(mine, theirs)) if a != b]
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_render_gpu.py"), "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+if __name__ == "__main__":
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    if len(sys.argv) == 4 and sys.argv[1] == "hashes":
+        json.dump(_frame_hashes(sys.argv[2]), open(sys.argv[3], "w"))
