@@ -18,7 +18,7 @@ EXPORTS = [
     "d2r_model_load", "d2r_model_free", "d2r_model_set_min_transmittance", "d2r_model_get_bitfield", "d2r_model_get_occupied_aabb",
     "d2r_view_prepare", "d2r_view_free", "d2r_view_get_dirs",
     "d2r_render", "d2r_render_ex", "d2r_render_composite", "d2r_render_composite_ex",
-    "d2r_clip_preprocess", "d2r_clip_preprocess_delta", "d2r_clip_load", "d2r_clip_free", "d2r_clip_encode", "d2r_score", "d2r_gemm_f16", "d2r_profile_enable", "d2r_profile_read", "d2r_profile_read_stats",
+    "d2r_clip_preprocess", "d2r_clip_preprocess_delta", "d2r_clip_load", "d2r_clip_free", "d2r_clip_encode", "d2r_score", "d2r_phys_check", "d2r_gemm_f16", "d2r_profile_enable", "d2r_profile_read", "d2r_profile_read_stats",
     "d2r_last_error", "d2r_launch_count", "d2r_version",
 ]
 
@@ -41,6 +41,11 @@ class ClipCfg(C.Structure):
     _fields_ = [("image_size", C.c_int32), ("patch_size", C.c_int32), ("hidden", C.c_int32), ("heads", C.c_int32),
                 ("layers", C.c_int32), ("mlp", C.c_int32), ("proj", C.c_int32), ("ln_eps", C.c_float),
                 ("max_batch", C.c_int32)]
+
+
+class PhysCfg(C.Structure):
+    _fields_ = [("dataset_scale", C.c_float), ("dataset_offset", C.c_float * 3), ("scene_centre_z", C.c_float),
+                ("unsup_thresh", C.c_float), ("p_dist", C.c_float), ("stability_check", C.c_int32)]
 
 
 _lib = None
@@ -78,6 +83,7 @@ def lib():
         "d2r_clip_free": (None, [vp]),
         "d2r_clip_encode": (i, [vp, vp, i, vp, vp]),
         "d2r_score": (i, [vp, vp, i, i, i, C.c_float, i, vp, vp, vp]),
+        "d2r_phys_check": (i, [vp, vp, i, vp, vp, vp, i, C.POINTER(PhysCfg), vp, vp]),
         "d2r_profile_enable": (i, [i, i]),
         "d2r_profile_read": (i, [i, vp, vp, vp, vp]),
         "d2r_profile_read_stats": (i, [i, vp]),

@@ -19,6 +19,7 @@ FAST = ["-ftz=true", "-prec-div=false", "-prec-sqrt=false"]
 SOURCES = {
     "d2r_model.cu": FAST,
     "d2r_march.cu": FAST,
+    "d2r_phys.cu": FAST,
     "d2r_post.cu": [],
     "d2r_gemm.cu": [],
     "d2r_clip.cu": [],

@@ -101,8 +101,14 @@ struct Ctx {
     size_t cap_split = 0;
     unsigned char* sp_feat = nullptr; float2* sp_aux = nullptr; uint4* sp_shb = nullptr; uint8_t* sp_nsb = nullptr;
     float* sp_t = nullptr; uint32_t* sp_live[2] = {nullptr, nullptr}; uint32_t* sp_cnt = nullptr;
+    float4* sp_acc4[2] = {nullptr, nullptr}; float* sp_acca[2] = {nullptr, nullptr};
+    // {hits, hit-list slots} of the latest finished launch, written by k_finish into host-mapped memory: sizes the per-round
+    // buffers of the split kernels by what launches actually hit instead of by their screen rectangles (no read-back: the
+    // host just looks at what has landed; a wrong guess costs speed, never correctness -- SplitParams::cap)
+    volatile uint32_t* fb_host = nullptr; uint32_t* fb_dev = nullptr;
+    double hit_ratio = 0.6;
+    size_t cap_t = 0;
 };
-constexpr int SPLIT_MAX_ROUNDS = MARCH_ITER / 2 + 2;
 static std::mutex g_ctx_mutex;
 static std::map<std::pair<int, cudaStream_t>, Ctx*> g_ctx;
 
@@ -134,6 +140,13 @@ static int ensure_ctx(Ctx& s, int K, int W, int H) {
         s.up_cap = cap;
     }
     if (!s.entry_counters) D2R_CUDA(cudaMalloc(&s.entry_counters, 2 * sizeof(uint32_t)));
+    if (!s.fb_host) {
+        void* h = nullptr;
+        D2R_CUDA(cudaHostAlloc(&h, 2 * sizeof(uint32_t), cudaHostAllocMapped));
+        memset(h, 0, 2 * sizeof(uint32_t));
+        s.fb_host = (volatile uint32_t*)h;
+        D2R_CUDA(cudaHostGetDevicePointer((void**)&s.fb_dev, h, 0));
+    }
     if ((size_t)W * H * 3 > s.cap_bg) {
         cudaFree(s.bg_u8);
         s.bg_u8 = nullptr; s.cap_bg = 0;
@@ -290,10 +303,78 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     count_launch(2);
     if (evp) D2R_CUDA(cudaEventRecord(evp->first, stream));   // time the march kernel alone
 
-    // D2R_MARCH=split: the per-round kernel pair of round 1 (A/B measurements; reads a live count back every 4th round)
-    static const bool use_split = []() { const char* e = getenv("D2R_MARCH"); return e && strcmp(e, "split") == 0; }();
-    D2R_REQUIRE(!(use_split && cost_out), "render: the Cost output is not available with D2R_MARCH=split");
-    if (!use_split) {
+    // Large launches: the first rounds -- where nearly every ray is still alive -- run as k_gather_round / k_mlp_round pairs, each
+    // kernel with the whole SM to itself (28 gather warps per SM; d2r_march_split.cuh); a FIXED number of them, so nothing is
+    // read back.  Whatever is still alive after that, and every small launch as a whole, goes through the persistent
+    // warp-specialised k_march_ws, which runs its rays to the end on the device.  Same arithmetic per sample in both: which
+    // kernel takes a sample never shows in the frames.
+    // D2R_MARCH=ws | split force one kernel for every launch (split: its tail still goes through k_march_ws).
+    static const int mode = []() { const char* e = getenv("D2R_MARCH"); return !e || !*e ? 0 : strcmp(e, "ws") == 0 ? 1 : strcmp(e, "split") == 0 ? 2 : 0; }();
+    static const int split_rounds = []() { const char* e = getenv("D2R_SPLIT_ROUNDS"); const int v = e ? atoi(e) : 16; return v >= 1 && v <= 256 ? v : 16; }();
+    constexpr size_t SPLIT_MIN_RAYS = 1u << 20;
+    const bool use_split = !cost_out && (mode == 2 || (mode == 0 && need >= SPLIT_MIN_RAYS));
+    P.work_list = nullptr; P.work_count = nullptr; P.t_cur = nullptr; P.resume_acc4 = nullptr; P.resume_acca = nullptr; P.resume_steps = 0;
+    P.split_cap = 0; P.feedback = s.fb_dev;
+    if (use_split) {
+        // how many of the rectangle pixels hit something: from the launches that have finished so far (hits / slots they asked for)
+        {
+            const uint32_t hits = s.fb_host[0], slots = s.fb_host[1];
+            if (slots) s.hit_ratio = std::min(1.0, std::max(0.05, 1.25 * (double)hits / (double)slots));
+        }
+        const size_t want = std::min(need, (size_t)(s.hit_ratio * (double)need) + 4096);
+        if (want > s.cap_split) {
+            cudaFree(s.sp_feat); cudaFree(s.sp_aux); cudaFree(s.sp_shb); cudaFree(s.sp_nsb);
+            cudaFree(s.sp_live[0]); cudaFree(s.sp_live[1]);
+            cudaFree(s.sp_acc4[0]); cudaFree(s.sp_acc4[1]); cudaFree(s.sp_acca[0]); cudaFree(s.sp_acca[1]);
+            s.sp_acc4[0] = s.sp_acc4[1] = nullptr; s.sp_acca[0] = s.sp_acca[1] = nullptr;
+            s.sp_feat = nullptr; s.sp_aux = nullptr; s.sp_shb = nullptr; s.sp_nsb = nullptr;
+            s.sp_live[0] = s.sp_live[1] = nullptr;
+            s.cap_split = 0;       // a failed allocation below must not leave a stale capacity behind
+            const size_t cap = want + want / 8, blocks = (cap + 127) / 128;
+            D2R_CUDA(cudaMalloc(&s.sp_feat, blocks * 2 * SPLIT_TILE_BYTES));
+            D2R_CUDA(cudaMalloc(&s.sp_aux, blocks * 2 * 128 * sizeof(float2)));
+            D2R_CUDA(cudaMalloc(&s.sp_shb, blocks * 128 * 2 * sizeof(uint4)));
+            D2R_CUDA(cudaMalloc(&s.sp_nsb, blocks * 128));
+            D2R_CUDA(cudaMalloc(&s.sp_live[0], cap * sizeof(uint32_t)));
+            D2R_CUDA(cudaMalloc(&s.sp_live[1], cap * sizeof(uint32_t)));
+            for (int i = 0; i < 2; ++i) {
+                D2R_CUDA(cudaMalloc(&s.sp_acc4[i], cap * sizeof(float4)));
+                D2R_CUDA(cudaMalloc(&s.sp_acca[i], cap * sizeof(float)));
+            }
+            s.cap_split = blocks * 128;
+        }
+        if (s.cap_entries > s.cap_t) {      // the ray parameter is kept by entry id
+            cudaFree(s.sp_t);
+            s.sp_t = nullptr; s.cap_t = 0;
+            D2R_CUDA(cudaMalloc(&s.sp_t, s.cap_entries * sizeof(float)));
+            s.cap_t = s.cap_entries;
+        }
+        if (!s.sp_cnt) D2R_CUDA(cudaMalloc(&s.sp_cnt, (256 + 2) * sizeof(uint32_t)));
+        D2R_CUDA(cudaMemsetAsync(s.sp_cnt, 0, (256 + 2) * sizeof(uint32_t), stream));
+        static bool split_attr[16] = {false};
+        if (!split_attr[m->device]) {
+            D2R_CUDA(cudaFuncSetAttribute(k_mlp_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
+            split_attr[m->device] = true;
+        }
+        SplitParams Q;
+        Q.feat = s.sp_feat; Q.aux = s.sp_aux; Q.shb = s.sp_shb; Q.nsb = s.sp_nsb; Q.t_cur = s.sp_t;
+        Q.cap = (uint32_t)std::min<size_t>(s.cap_split, 0xffffffffu);
+        P.split_cap = Q.cap;
+        for (int r = 0; r < split_rounds; ++r) {
+            Q.round = r;
+            Q.cnt_in = s.sp_cnt + r; Q.cnt_out = s.sp_cnt + r + 1;
+            Q.live_in = s.sp_live[r & 1]; Q.live_out = s.sp_live[(r + 1) & 1];
+            Q.acc4_in = s.sp_acc4[r & 1]; Q.acca_in = s.sp_acca[r & 1]; Q.acc4_out = s.sp_acc4[(r + 1) & 1]; Q.acca_out = s.sp_acca[(r + 1) & 1];
+            k_gather_round<<<s.n_sm * 7, 128, 0, stream>>>(P, Q);
+            k_mlp_round<<<s.n_sm * 3, TC_THREADS, T2_TOTAL, stream>>>(P, Q);
+            count_launch(2);
+        }
+        // the survivors: a live ray of round r has taken exactly 2 r samples
+        P.work_list = s.sp_live[split_rounds & 1]; P.work_count = s.sp_cnt + split_rounds; P.t_cur = s.sp_t;
+        P.resume_acc4 = s.sp_acc4[split_rounds & 1]; P.resume_acca = s.sp_acca[split_rounds & 1];
+        P.resume_steps = 2 * split_rounds;
+    }
+    {
         static bool attr_set[16] = {false};
         if (!attr_set[m->device]) {
             D2R_CUDA(cudaFuncSetAttribute(k_march_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_TOTAL));
@@ -305,48 +386,9 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
         if (want_stats && P.prof) k_march_ws<true><<<s.n_sm, WS_THREADS, WS_TOTAL, stream>>>(P);
         else k_march_ws<false><<<s.n_sm, WS_THREADS, WS_TOTAL, stream>>>(P);
         count_launch();
-    } else {
-        if (need > s.cap_split) {
-            cudaFree(s.sp_feat); cudaFree(s.sp_aux); cudaFree(s.sp_shb); cudaFree(s.sp_nsb); cudaFree(s.sp_t);
-            cudaFree(s.sp_live[0]); cudaFree(s.sp_live[1]);
-            s.sp_feat = nullptr; s.sp_aux = nullptr; s.sp_shb = nullptr; s.sp_nsb = nullptr; s.sp_t = nullptr;
-            s.sp_live[0] = s.sp_live[1] = nullptr;
-            s.cap_split = 0;       // a failed allocation below must not leave a stale capacity behind
-            const size_t blocks = (need + 127) / 128;
-            D2R_CUDA(cudaMalloc(&s.sp_feat, blocks * 2 * SPLIT_TILE_BYTES));
-            D2R_CUDA(cudaMalloc(&s.sp_aux, blocks * 2 * 128 * sizeof(float2)));
-            D2R_CUDA(cudaMalloc(&s.sp_shb, need * 2 * sizeof(uint4)));
-            D2R_CUDA(cudaMalloc(&s.sp_nsb, blocks * 128));
-            D2R_CUDA(cudaMalloc(&s.sp_t, need * sizeof(float)));
-            D2R_CUDA(cudaMalloc(&s.sp_live[0], need * sizeof(uint32_t)));
-            D2R_CUDA(cudaMalloc(&s.sp_live[1], need * sizeof(uint32_t)));
-            s.cap_split = need;
-        }
-        if (!s.sp_cnt) D2R_CUDA(cudaMalloc(&s.sp_cnt, (SPLIT_MAX_ROUNDS + 2) * sizeof(uint32_t)));
-        D2R_CUDA(cudaMemsetAsync(s.sp_cnt, 0, (SPLIT_MAX_ROUNDS + 2) * sizeof(uint32_t), stream));
-        static bool split_attr[16] = {false};
-        if (!split_attr[m->device]) {
-            D2R_CUDA(cudaFuncSetAttribute(k_mlp_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
-            split_attr[m->device] = true;
-        }
-        SplitParams Q;
-        Q.feat = s.sp_feat; Q.aux = s.sp_aux; Q.shb = s.sp_shb; Q.nsb = s.sp_nsb; Q.t_cur = s.sp_t;
-        for (int r = 0; r < SPLIT_MAX_ROUNDS; ++r) {
-            Q.round = r;
-            Q.cnt_in = s.sp_cnt + r; Q.cnt_out = s.sp_cnt + r + 1;
-            Q.live_in = s.sp_live[r & 1]; Q.live_out = s.sp_live[(r + 1) & 1];
-            k_gather_round<<<s.n_sm * 7, 128, 0, stream>>>(P, Q);
-            k_mlp_round<<<s.n_sm * 4, TC_THREADS, T2_TOTAL, stream>>>(P, Q);
-            count_launch(2);
-            if (r >= 7 && (r & 3) == 3) {       // every 4th round from round 7 on: is anything left?  (one 4-byte read-back)
-                uint32_t left = 0;
-                D2R_CUDA(cudaMemcpyAsync(&left, s.sp_cnt + r + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-                D2R_CUDA(cudaStreamSynchronize(stream));
-                if (!left) break;
-            }
-        }
     }
     if (evp) D2R_CUDA(cudaEventRecord(evp->second, stream));
+    P.feedback_slots = (uint32_t)std::min<size_t>(need, 0xffffffffu);
     k_finish<<<s.n_sm * 8, 256, 0, stream>>>(P);
     count_launch();
     D2R_CUDA(cudaGetLastError());

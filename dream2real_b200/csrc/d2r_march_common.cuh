@@ -39,6 +39,18 @@ struct MarchParams {
     uint32_t* entry_cursor;        //   consumption cursor (device)
     float4* res_rgbd;              //   per-entry accumulated (r, g, b, depth), written by the march kernel
     float* res_a;                  //   per-entry accumulated alpha
+    // k_march_ws work: entry ids to march (null = every hit-list entry) and how many; resume_steps > 0: the rays come out of
+    // `resume_steps / 2` rounds of the split kernels -- ray parameter from t_cur (by entry id), accumulators from resume_acc4 /
+    // resume_acca (by position in work_list)
+    const uint32_t* work_list;
+    const uint32_t* work_count;
+    const float* t_cur;
+    const float4* resume_acc4;
+    const float* resume_acca;
+    int resume_steps;
+    uint32_t split_cap;            //   the split rounds only ran if the launch has at most this many hits
+    uint32_t* feedback;            // host-mapped {hits, hit-list slots asked for} of this launch, written by k_finish, or null
+    uint32_t feedback_slots;
     float* res_n;                  //   per-entry step count as the reference's payload.n_steps ends up (Cost render mode), or null
     float* cost_out;               // [K,H,W] or null   (Cost: n_steps of the rays the reference keeps, 0 elsewhere)
 };
@@ -209,10 +221,56 @@ __device__ __forceinline__ void finish_ray(const MarchParams& P, float cr, float
 // Pass 3: one thread per hit-list entry, every lane busy.
 __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ MarchParams P) {
     const uint32_t n = *P.n_entries;
+    if (P.feedback && blockIdx.x == 0 && threadIdx.x == 0) { P.feedback[1] = P.feedback_slots; P.feedback[0] = n; __threadfence_system(); }
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const RayEntry e = P.entries[i];
         const float4 c = P.res_rgbd[i];
         finish_ray(P, c.x, c.y, c.z, c.w, P.res_a[i], P.res_n ? P.res_n[i] : 0.f, e.idx, e.k);
+    }
+}
+
+// plain (non-tensor) bulk copy global -> shared memory of this CTA, completion on an mbarrier (complete_tx::bytes)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// D[tmem] (+)= A . B^T with the two smem descriptors passed as 32-bit halves (no 64-bit arithmetic on the issuing thread's
+// critical path): lo = (address >> 4) | LBO field, hi = SBO field | version
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_ss_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+}
+// one MLP layer for ONE 128-row tile: K/16 MMAs, fully unrolled
+template <int K, int N>
+__device__ __forceinline__ void issue_tile_ws(uint32_t a_lo, uint32_t b_lo, uint32_t tmem_d) {
+    constexpr uint32_t hi = (uint32_t)((K / 8) * 128 >> 4) | (1u << 14);      // SBO | descriptor version 1 (bit 46)
+    constexpr uint32_t idesc = umma_idesc_f16(128, N, 0);
+    umma_f16_ss_lohi<false>(tmem_d, a_lo, b_lo, hi, idesc);
+#pragma unroll
+    for (int kk = 1; kk < K / 16; ++kk) umma_f16_ss_lohi<true>(tmem_d, a_lo + kk * 16, b_lo + kk * 16, hi, idesc);
+}
+// one MLP layer for both sample tiles of a group: 2 x K/16 MMAs, fully unrolled
+template <int K, int N>
+__device__ __forceinline__ void issue_layer_ws(uint32_t a_lo, uint32_t b_lo, uint32_t tmem_d) {
+    constexpr uint32_t hi = (uint32_t)((K / 8) * 128 >> 4) | (1u << 14);      // SBO | descriptor version 1 (bit 46)
+    constexpr uint32_t idesc = umma_idesc_f16(128, N, 0);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        umma_f16_ss_lohi<false>(tmem_d + s * 64, a_lo + s * 1024, b_lo, hi, idesc);
+#pragma unroll
+        for (int kk = 1; kk < K / 16; ++kk) umma_f16_ss_lohi<true>(tmem_d + s * 64, a_lo + s * 1024 + kk * 16, b_lo + kk * 16, hi, idesc);
     }
 }
 

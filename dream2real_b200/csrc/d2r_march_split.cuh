@@ -25,16 +25,22 @@ struct SplitParams {
     uint32_t* live_out;
     unsigned char* feat;        // [block][2][8 KB]: sample tile = 128 rows x 32 fp16 in UMMA canonical K-major layout
     float2* aux;                // [block][2][128]: (depth of the sample, unwarped dt)
-    uint4* shb;                 // [entries][2]: 16 fp16 SH coefficients of the ray direction (written in round 0)
+    uint4* shb;                 // [block*128][2]: 16 fp16 SH coefficients of the ray direction, by position in this round's list
+    const float4* acc4_in;      // [block*128]: accumulated (r, g, b, depth) of the ray at this position (rounds > 0) ...
+    const float* acca_in;       //              ... and its accumulated alpha
+    float4* acc4_out;           // the same for the next round's list, written where k_mlp_round appends the ray
+    float* acca_out;
     uint8_t* nsb;               // [block*128]: samples prepared (0..2) | 16 if the ray leaves the occupied region after them
     float* t_cur;               // [entries]: ray parameter after the samples taken so far
-};
+    uint32_t cap;               // positions the per-round buffers hold; a launch with more hits than that skips the split rounds
+};                              // on the device (k_march_ws then takes every ray from the start)
 
 constexpr int SPLIT_TILE_BYTES = 128 * 32 * 2;
 
 __global__ void __launch_bounds__(128, 7) k_gather_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
     const ModelDev& M = P.M;
     const int tid = threadIdx.x;
+    if (*P.n_entries > Q.cap) return;
     const uint32_t n_live = Q.round == 0 ? *P.n_entries : *Q.cnt_in;
     const StepC cone = make_stepc(M.cone);
     const uint32_t max_mip = (uint32_t)M.max_cascade;
@@ -51,7 +57,7 @@ __global__ void __launch_bounds__(128, 7) k_gather_round(const __grid_constant__
         g.t_exit = en.t_exit;
         float t = Q.round == 0 ? en.t : Q.t_cur[e];
         const float fwx = C.c[2][0], fwy = C.c[2][1], fwz = C.c[2][2];
-        if (Q.round == 0 && valid) {          // SH coefficients of the ray direction: once per ray, kept by entry id
+        {   // SH coefficients of the ray direction, by position like everything else k_mlp_round reads: its inputs are contiguous
             float sh[16];
             const float wx = (g.dx + 1.0f) * 0.5f, wy = (g.dy + 1.0f) * 0.5f, wz = (g.dz + 1.0f) * 0.5f;
             sh_enc4(wx * 2.f - 1.f, wy * 2.f - 1.f, wz * 2.f - 1.f, sh);
@@ -61,8 +67,8 @@ __global__ void __launch_bounds__(128, 7) k_gather_round(const __grid_constant__
                 __half2 h = __floats2half2_rn(sh[2 * j], sh[2 * j + 1]);
                 pk[j] = *reinterpret_cast<uint32_t*>(&h);
             }
-            Q.shb[(size_t)e * 2] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            Q.shb[(size_t)e * 2 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            Q.shb[(size_t)i * 2] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            Q.shb[(size_t)i * 2 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
         // the walk of k_march_ws (phase B), verbatim
         int n_s = 0;
@@ -126,24 +132,30 @@ __global__ void __launch_bounds__(128, 7) k_gather_round(const __grid_constant__
     (void)my_samples;
 }
 
-// shared memory plan of k_mlp_round (bytes): weights, then 2 tiles whose K=32 and K=64 operands alias (52 KB -> 4 CTAs per SM)
+// shared memory plan of k_mlp_round (bytes): weights, 2 tiles whose K=32 and K=64 operands alias, and the feature staging
+// buffer the bulk copies land in (68 KB -> 3 CTAs per SM)
 constexpr int T2_A64 = W_BYTES;
 constexpr int T2_A32 = T2_A64;
 constexpr int T2_TILE = 16384;
-constexpr int T2_MISC = T2_A64 + 2 * T2_TILE;
+constexpr int T2_FEAT = T2_A64 + 2 * T2_TILE;          // [2][8 KB]: a block's two sample tiles exactly as k_gather_round wrote them
+constexpr int T2_MISC = T2_FEAT + 2 * SPLIT_TILE_BYTES;
 constexpr int T2_TOTAL = T2_MISC + 256;
 
-// feature rows are fetched without waiting for the per-ray sample count, and a block's live-list append is finished during
-// the next block's first MMA wait (the atomic's round trip is off the critical path)
-__global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
+// A block's two feature tiles (16 KB, contiguous, already in UMMA operand layout) arrive with ONE cp.async.bulk straight into the
+// buffer the first layer's MMAs read: no thread touches them.  The copy for the next block is issued as soon as those MMAs
+// have retired, so it flies during the other four layers; a block's live-list append is finished during the next block's
+// first MMA wait (the atomic's round trip is off the critical path).
+__global__ void __launch_bounds__(TC_THREADS, 3) k_mlp_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
     extern __shared__ __align__(128) unsigned char smem[];
+    if (*P.n_entries > Q.cap) return;
     const ModelDev& M = P.M;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + T2_MISC);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T2_MISC + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T2_MISC + 16);      // (mbarriers at +0, +8, +24)
 
     for (int i = tid; i < W_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(M.w_umma)[i];
-    if (tid == 0) { mbar_init(mbar, 1); fence_barrier_init(); }
+    uint64_t* bar_feat = mbar + 3;
+    if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); mbar_init(bar_feat, 1); fence_barrier_init(); }
     if (warp == 0) tmem_alloc<128>(tmem_slot);
     fence_proxy_async();
     tc_fence_before();
@@ -151,88 +163,75 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const uint32_t a32 = smem_u32(smem + T2_A32), a64 = smem_u32(smem + T2_A64);
-    const uint32_t wd0 = smem_u32(smem + W_D0), wd1 = smem_u32(smem + W_D1), wc0 = smem_u32(smem + W_C0),
-                   wc1 = smem_u32(smem + W_C1), wc2 = smem_u32(smem + W_C2);
+    const uint32_t a64 = smem_u32(smem + T2_A64);
     unsigned char* rowA32 = smem + T2_A32 + umma_chunk_off(tid, 0, 32);
     unsigned char* rowA64 = smem + T2_A64 + umma_chunk_off(tid, 0, 64);
-    uint32_t phase = 0;
+    uint32_t phase0 = 0, phase1 = 0, phase_feat = 0;
     const uint32_t n_live = Q.round == 0 ? *P.n_entries : *Q.cnt_in;
-    unsigned long long my_samples = 0, my_rays = 0;
-    auto issue2 = [&](uint32_t a_addr, uint32_t a_tile_bytes, uint32_t b_addr, int K, int N) {
-        const uint32_t idesc = umma_idesc_f16(128, N, 0);
-        const uint32_t sbo = (uint32_t)(K / 8) * 128;
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
-            for (int kk = 0; kk < K / 16; ++kk) {
-                const uint64_t da = umma_desc_noswz(a_addr + s * a_tile_bytes + kk * 256, 128, sbo);
-                const uint64_t db = umma_desc_noswz(b_addr + kk * 256, 128, sbo);
-                umma_f16_ss(tmem_base + s * 64, da, db, idesc, kk > 0);
-            }
-        }
-        tc_commit(mbar);
+    const uint32_t f_lo = (smem_u32(smem + T2_FEAT) >> 4) + (8u << 16);
+    auto fetch_features = [&](uint32_t b) {      // tid 0: the two sample tiles of block b -> staging buffer
+        mbar_arrive_expect_tx(bar_feat, 2 * SPLIT_TILE_BYTES);
+        bulk_g2s(smem + T2_FEAT, Q.feat + (size_t)b * 2 * SPLIT_TILE_BYTES, 2 * SPLIT_TILE_BYTES, bar_feat);
     };
-
-    uint32_t pend_go = 0, pend_base = 0, pend_e = 0;      // the previous block's live-list append, atomic already issued
+    if (tid == 0 && (size_t)blockIdx.x * 128 < n_live) fetch_features(blockIdx.x);
+    unsigned long long my_samples = 0, my_rays = 0;
+    // descriptor low words ((address >> 4) | LBO 128 B): the issuing thread's path is a handful of 32-bit adds per MMA
+    const uint32_t a_lo = (a64 >> 4) + (8u << 16), w_lo = (smem_u32(smem) >> 4) + (8u << 16);
+    // the previous block's live-list append (its atomic is already in flight): entry id and accumulators of the rays that go on
+    uint32_t pend_go = 0, pend_base = 0, pend_e = 0;
     bool pend_alive = false;
+    float4 pend_a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float pend_aa = 0.f;
     auto flush_append = [&]() {
         if (pend_go) {
             const uint32_t base = __shfl_sync(0xffffffffu, pend_base, __ffs(pend_go) - 1);
-            if (pend_alive) Q.live_out[base + __popc(pend_go & ((1u << lane) - 1))] = pend_e;
+            if (pend_alive) {
+                const uint32_t pos = base + __popc(pend_go & ((1u << lane) - 1));
+                Q.live_out[pos] = pend_e;
+                Q.acc4_out[pos] = pend_a4;
+                Q.acca_out[pos] = pend_aa;
+            }
             pend_go = 0;
         }
     };
+    // Everything a block reads per ray is indexed by the ray's POSITION in this round's list (coalesced), and is fetched one
+    // block ahead: the loads are issued after the last proxy fence of the previous block, so no fence ever waits for them.
+    struct In { uint32_t ns_raw, e; uint4 sh0, sh1; float2 ax0, ax1; float4 a4; float aa; };
+    auto load_inputs = [&](uint32_t b) {
+        In in;
+        const uint32_t i = b * 128 + tid;
+        in.ns_raw = 0u; in.e = 0u; in.sh0 = in.sh1 = make_uint4(0, 0, 0, 0); in.ax0 = in.ax1 = make_float2(0.f, 0.f);
+        in.a4 = make_float4(0.f, 0.f, 0.f, 0.f); in.aa = 0.f;
+        if (i < n_live) {
+            in.ns_raw = Q.nsb[i] | 0x100u;                                   // bit 8: a ray sits at this position
+            in.e = Q.round == 0 ? i : Q.live_in[i];
+            in.sh0 = Q.shb[(size_t)i * 2]; in.sh1 = Q.shb[(size_t)i * 2 + 1];
+            in.ax0 = Q.aux[((size_t)b * 2 + 0) * 128 + tid];
+            in.ax1 = Q.aux[((size_t)b * 2 + 1) * 128 + tid];
+            if (Q.round > 0) { in.a4 = Q.acc4_in[i]; in.aa = Q.acca_in[i]; }
+        }
+        return in;
+    };
+    In nxt = load_inputs(blockIdx.x);
     for (uint32_t blk = blockIdx.x; (size_t)blk * 128 < n_live; blk += gridDim.x) {
-        const uint32_t i = blk * 128 + tid;
-        const bool valid = i < n_live;
-        const uint32_t ns_raw = valid ? Q.nsb[i] : 0u;
-        const int n_s = (int)(ns_raw & 15u);
-        const bool exits = (ns_raw & 16u) != 0;
-        const uint32_t e = valid ? (Q.round == 0 ? i : Q.live_in[i]) : 0u;
-        {   // the next block's inputs come from HBM (a round's features do not fit the L2): start them towards the L2 now
-            const uint32_t nb = blk + 2 * gridDim.x;            // two blocks ahead (the first two blocks of a CTA go unprefetched)
-            if ((size_t)nb * 128 < n_live) {
-                const unsigned char* f = Q.feat + (size_t)nb * 2 * SPLIT_TILE_BYTES + (size_t)tid * 128;     // 16 KB = 128 lines
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(f));
-                if (tid < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char*>(Q.aux + (size_t)nb * 2 * 128) + tid * 128));
-            }
-        }
-        // this slot's rows of the two sample tiles: already in operand layout, 4 x 16 bytes each
-        {
-            const unsigned char* src = Q.feat + (size_t)blk * 2 * SPLIT_TILE_BYTES + umma_chunk_off(tid, 0, 32);
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (valid) v = *reinterpret_cast<const uint4*>(src + s * SPLIT_TILE_BYTES + c * 128);
-                    *reinterpret_cast<uint4*>(rowA32 + s * T2_TILE + c * 128) = v;
-                }
-            }
-        }
-        float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, ca = 0.f;
-        if (valid && Q.round > 0) {
-            const float4 a = P.res_rgbd[e];
-            cr = a.x; cg = a.y; cb = a.z; cd = a.w; ca = P.res_a[e];
-        }
-        uint4 sh0 = make_uint4(0, 0, 0, 0), sh1 = sh0;
-        float2 ax0 = make_float2(0.f, 0.f), ax1 = ax0;
-        if (valid) {
-            sh0 = Q.shb[(size_t)e * 2]; sh1 = Q.shb[(size_t)e * 2 + 1];
-            ax0 = Q.aux[((size_t)blk * 2 + 0) * 128 + tid];
-            ax1 = Q.aux[((size_t)blk * 2 + 1) * 128 + tid];
-        }
+        const In cur = nxt;
+        const bool valid = (cur.ns_raw & 0x100u) != 0;
+        const int n_s = (int)(cur.ns_raw & 15u);
+        const bool exits = (cur.ns_raw & 16u) != 0;
+        const uint32_t e = cur.e;
+        float cr = cur.a4.x, cg = cur.a4.y, cb = cur.a4.z, cd = cur.a4.w, ca = cur.aa;
+        const uint4 sh0 = cur.sh0, sh1 = cur.sh1;
+        const float2 ax0 = cur.ax0, ax1 = cur.ax1;
         if (valid && Q.round == 0) ++my_rays;
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        // ---- density layer 0: 32 -> 64, ReLU ----
-        if (tid == 0) { tc_fence_after(); issue2(a32, T2_TILE, wd0, 32, 64); }
-        flush_append();          // the previous block's append: its atomic returned long ago
-        mbar_wait(mbar, phase); phase ^= 1;
-        tc_fence_after();
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
+        // The five layers, the two sample tiles skewed against each other: each tile has its own mbarrier and its own TMEM
+        // columns, and the MMAs of one tile's next layer are issued the moment its rows are written -- they run while every
+        // thread is busy with the other tile's tcgen05.ld / ReLU / fp16 pack / store.  (Issuing is a handful of 32-bit adds
+        // per MMA: issue_tile_ws.)
+        auto wait_tile = [&](int s) {
+            if (s == 0) { mbar_wait(mbar, phase0); phase0 ^= 1; } else { mbar_wait(mbar + 1, phase1); phase1 ^= 1; }
+            tc_fence_after();
+        };
+        auto hidden_rows = [&](int s) {      // 64 outputs, ReLU, fp16 -> the tile's K=64 operand rows
             uint32_t r[64];
             tmem_ld_32x32_x64(tmem_lane + s * 64, r);
             tmem_ld_wait();
@@ -243,15 +242,33 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
                 v.z = pack_relu_h2(r[8 * c + 4], r[8 * c + 5], true); v.w = pack_relu_h2(r[8 * c + 6], r[8 * c + 7], true);
                 *reinterpret_cast<uint4*>(rowA64 + s * T2_TILE + c * 128) = v;
             }
+        };
+        auto rows_done = [&]() { fence_proxy_async(); tc_fence_before(); __syncthreads(); };
+        // ---- density layer 0: 32 -> 64, ReLU; A = the staged feature tiles ----
+        if (tid == 0) {
+            mbar_wait(bar_feat, phase_feat);
+            tc_fence_after();
+            issue_tile_ws<32, 64>(f_lo, w_lo + (W_D0 >> 4), tmem_base); tc_commit(mbar);
+            issue_tile_ws<32, 64>(f_lo + (SPLIT_TILE_BYTES >> 4), w_lo + (W_D0 >> 4), tmem_base + 64); tc_commit(mbar + 1);
         }
-        fence_proxy_async(); tc_fence_before(); __syncthreads();
-        // ---- density layer 1: 64 -> 16 (row 0 = raw density); rgb input = [16 density-out | 16 SH] ----
-        if (tid == 0) { tc_fence_after(); issue2(a64, T2_TILE, wd1, 64, 16); }
-        mbar_wait(mbar, phase); phase ^= 1;
-        tc_fence_after();
-        float sigma0 = 0.f, sigma1 = 0.f;
-#pragma unroll 1
+        phase_feat ^= 1;
+        flush_append();          // the previous block's append: its atomic returned long ago
+#pragma unroll
         for (int s = 0; s < 2; ++s) {
+            wait_tile(s);
+            if (s == 1 && tid == 0) {      // both tiles' first-layer MMAs have retired: the staging buffer is free for the next block
+                const uint32_t nb = blk + gridDim.x;
+                if ((size_t)nb * 128 < n_live) fetch_features(nb);
+            }
+            hidden_rows(s);
+            rows_done();
+            // ---- density layer 1: 64 -> 16 (row 0 = raw density) ----
+            if (tid == 0) { tc_fence_after(); issue_tile_ws<64, 16>(a_lo + s * 1024, w_lo + (W_D1 >> 4), tmem_base + s * 64); tc_commit(mbar + s); }
+        }
+        float sigma0 = 0.f, sigma1 = 0.f;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            wait_tile(s);
             uint32_t r[16];
             tmem_ld_32x32_x16(tmem_lane + s * 64, r);
             tmem_ld_wait();
@@ -262,56 +279,38 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
             v0.z = pack_relu_h2(r[4], r[5], false); v0.w = pack_relu_h2(r[6], r[7], false);
             v1.x = pack_relu_h2(r[8], r[9], false); v1.y = pack_relu_h2(r[10], r[11], false);
             v1.z = pack_relu_h2(r[12], r[13], false); v1.w = pack_relu_h2(r[14], r[15], false);
-            unsigned char* row = rowA32 + s * T2_TILE;
+            unsigned char* row = rowA32 + s * T2_TILE;      // rgb input = [16 density-out | 16 SH]
             *reinterpret_cast<uint4*>(row + 0) = v0;
             *reinterpret_cast<uint4*>(row + 128) = v1;
             *reinterpret_cast<uint4*>(row + 256) = sh0;
             *reinterpret_cast<uint4*>(row + 384) = sh1;
+            rows_done();
+            // ---- rgb layer 0: 32 -> 64, ReLU ----
+            if (tid == 0) { tc_fence_after(); issue_tile_ws<32, 64>(a_lo + s * 1024, w_lo + (W_C0 >> 4), tmem_base + s * 64); tc_commit(mbar + s); }
         }
-        fence_proxy_async(); tc_fence_before(); __syncthreads();
-        // ---- rgb layer 0: 32 -> 64, ReLU ----
-        if (tid == 0) { tc_fence_after(); issue2(a32, T2_TILE, wc0, 32, 64); }
-        mbar_wait(mbar, phase); phase ^= 1;
-        tc_fence_after();
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
-            uint32_t r[64];
-            tmem_ld_32x32_x64(tmem_lane + s * 64, r);
-            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint4 v;
-                v.x = pack_relu_h2(r[8 * c + 0], r[8 * c + 1], true); v.y = pack_relu_h2(r[8 * c + 2], r[8 * c + 3], true);
-                v.z = pack_relu_h2(r[8 * c + 4], r[8 * c + 5], true); v.w = pack_relu_h2(r[8 * c + 6], r[8 * c + 7], true);
-                *reinterpret_cast<uint4*>(rowA64 + s * T2_TILE + c * 128) = v;
-            }
-        }
-        fence_proxy_async(); tc_fence_before(); __syncthreads();
-        // ---- rgb layer 1: 64 -> 64, ReLU ----
-        if (tid == 0) { tc_fence_after(); issue2(a64, T2_TILE, wc1, 64, 64); }
-        mbar_wait(mbar, phase); phase ^= 1;
-        tc_fence_after();
-#pragma unroll 1
         for (int s = 0; s < 2; ++s) {
-            uint32_t r[64];
-            tmem_ld_32x32_x64(tmem_lane + s * 64, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint4 v;
-                v.x = pack_relu_h2(r[8 * c + 0], r[8 * c + 1], true); v.y = pack_relu_h2(r[8 * c + 2], r[8 * c + 3], true);
-                v.z = pack_relu_h2(r[8 * c + 4], r[8 * c + 5], true); v.w = pack_relu_h2(r[8 * c + 6], r[8 * c + 7], true);
-                *reinterpret_cast<uint4*>(rowA64 + s * T2_TILE + c * 128) = v;
-            }
+            wait_tile(s);
+            hidden_rows(s);
+            rows_done();
+            // ---- rgb layer 1: 64 -> 64, ReLU ----
+            if (tid == 0) { tc_fence_after(); issue_tile_ws<64, 64>(a_lo + s * 1024, w_lo + (W_C1 >> 4), tmem_base + s * 64); tc_commit(mbar + s); }
         }
-        fence_proxy_async(); tc_fence_before(); __syncthreads();
-        // ---- rgb output layer: 64 -> 16 (3 used) ----
-        if (tid == 0) { tc_fence_after(); issue2(a64, T2_TILE, wc2, 64, 16); }
-        mbar_wait(mbar, phase); phase ^= 1;
-        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            wait_tile(s);
+            hidden_rows(s);      // in place: the MMA that read these rows has retired
+            rows_done();
+            // ---- rgb output layer: 64 -> 16 (3 used) ----
+            if (tid == 0) { tc_fence_after(); issue_tile_ws<64, 16>(a_lo + s * 1024, w_lo + (W_C2 >> 4), tmem_base + s * 64); tc_commit(mbar + s); }
+        }
+        // that was this block's last proxy fence: the next block's per-ray inputs start their way now and land during the
+        // output layer, the compositing and the next block's first layer
+        nxt = load_inputs(blk + gridDim.x);
         float raw[2][3];
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
+            wait_tile(s);
             uint32_t r[16];
             tmem_ld_32x32_x16(tmem_lane + s * 64, r);
             tmem_ld_wait();
@@ -319,7 +318,6 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
         }
         // ---- composite_kernel_nerf (testbed_nerf.cu:511-667), sample 0 then sample 1; same arithmetic as k_march_ws ----
         bool alive = valid;
-        bool finished = false;
         if (alive) {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
@@ -333,16 +331,16 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
                     cr += rr * weight; cg += gg * weight; cb += bb_ * weight; cd += dep * weight; ca += weight;
                     if (ca > (1.0f - M.min_transmittance)) {
                         cr /= ca; cg /= ca; cb /= ca; cd /= ca; ca /= ca;
-                        alive = false; finished = true;
+                        alive = false;
                     } else if (2 * Q.round + s + 1 >= MARCH_ITER - 1) {      // a live ray of round r has taken 2 r samples
                         cr = cg = cb = cd = ca = 0.f;                          // never reaches the hit buffer in the reference
-                        alive = false; finished = true;
+                        alive = false;
                     }
                 }
             }
-            if (alive && (exits || n_s < 2)) { alive = false; finished = true; }   // ran out of occupied cells
+            if (alive && (exits || n_s < 2)) { alive = false; }   // ran out of occupied cells
         }
-        if (valid) {
+        if (valid && !alive) {      // finished: what k_finish turns into a pixel
             P.res_rgbd[e] = make_float4(cr, cg, cb, cd);
             P.res_a[e] = ca;
         }
@@ -353,9 +351,10 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_mlp_round(const __grid_consta
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(Q.cnt_out, (uint32_t)__popc(go));
             pend_go = go; pend_base = base; pend_alive = alive; pend_e = e;      // finished by flush_append()
+            pend_a4 = make_float4(cr, cg, cb, cd); pend_aa = ca;
         }
-        (void)finished;
-        __syncthreads();      // the A tiles are rewritten at the top of the next block
+        tc_fence_before();
+        __syncthreads();      // every thread has read its output rows: the next block's first MMAs may overwrite the TMEM columns
     }
     flush_append();
     tc_fence_before();

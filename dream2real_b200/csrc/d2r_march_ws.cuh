@@ -76,11 +76,11 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)      // suspend-time hint (ns): sleep in hardware, wake on completion
             : "memory");
         if (ok) return;
         const long long now = clock64();
@@ -102,11 +102,6 @@ __device__ __forceinline__ bool group_or(int id, bool v) {
         : "r"((uint32_t)v), "r"(id)
         : "memory");
     return r != 0;
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32_x32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
 
@@ -134,7 +129,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_march_ws(const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = mi->tmem_slot;
-    const uint32_t total_entries = *P.n_entries;
+    // rays resumed from the split rounds -- unless this launch had more hits than their buffers hold, in which case those
+    // kernels returned at once and every ray starts here
+    const bool resumed = P.resume_steps > 0 && *P.n_entries <= P.split_cap;
+    const uint32_t total_entries = resumed ? *P.work_count : *P.n_entries;
     unsigned long long my_samples = 0, my_rays = 0;
 
     if (warp < WS_NG * 4) {
@@ -159,6 +157,47 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_march_ws(const __grid_constan
         const bool st = STATS && lane == 0;
         long long c_wait = 0, c_walk = 0, c_enc = 0, c_refill = 0, c_rounds = 0;
         const long long c_begin = st ? clock64() : 0;
+        // the ray's next (up to) two samples: position in the network's input space, depth and step for compositing
+        int n_s = 0;
+        bool exits = false, walked = false;
+        float wp0x = 0.f, wp0y = 0.f, wp0z = 0.f, wp1x = 0.f, wp1y = 0.f, wp1z = 0.f;
+        float dep0 = 0.f, dep1 = 0.f, dtu0 = 0.f, dtu1 = 0.f;
+        // One walk loop for both samples (generate_next_nerf_network_inputs, testbed_nerf.cu:454-467, twice): the same sequence
+        // of operations on t as two calls of if_unoccupied_advance_to_next_occupied_voxel.  The next sample positions depend on
+        // the occupancy grid only, never on the network output, so a ray that may go on walks to them while its MLP round is
+        // still in flight; if the round turns out to saturate it, the walk was for nothing (like the unused tail of the
+        // reference's n_steps).
+        auto do_walk = [&]() {
+            n_s = 0;
+            exits = false;
+            while (true) {
+                const float px = G.ox + t * G.dx, py = G.oy + t * G.dy, pz = G.oz + t * G.dz;
+                if (t >= MAX_DEPTH() || t > G.t_exit || !raabb_contains(M, px, py, pz)) { exits = true; break; }
+                uint32_t mip = min(max(mip_from_pos(px, py, pz), 0u), max_mip);
+                if (density_grid_occupied_at(px, py, pz, M.bitfield_lin, mip)) {
+                    const float dt = calc_dt(t, cone);
+                    const float wx = (px - M.aabb_min[0]) / M.aabb_diag[0];
+                    const float wy = (py - M.aabb_min[1]) / M.aabb_diag[1];
+                    const float wz = (pz - M.aabb_min[2]) / M.aabb_diag[2];
+                    // composite_kernel_nerf reads the position back from the network input (unwarp_position) and the
+                    // step from warp_dt/unwarp_dt: same arithmetic here, evaluated before the MLP instead of after
+                    const float ux = M.aabb_min[0] + wx * M.aabb_diag[0];
+                    const float uy = M.aabb_min[1] + wy * M.aabb_diag[1];
+                    const float uz = M.aabb_min[2] + wz * M.aabb_diag[2];
+                    float dep = 0.f;
+                    dep += fwx * (ux - G.ox); dep += fwy * (uy - G.oy); dep += fwz * (uz - G.oz);
+                    dep *= M.depth_scale;
+                    const float dtu = unwarp_dt(warp_dt(dt));
+                    if (n_s == 0) { wp0x = wx; wp0y = wy; wp0z = wz; dep0 = dep; dtu0 = dtu; }
+                    else { wp1x = wx; wp1y = wy; wp1z = wz; dep1 = dep; dtu1 = dtu; }
+                    t += dt;
+                    if (++n_s == 2) break;
+                    continue;
+                }
+                while (mip < max_mip && !density_grid_occupied_at(px, py, pz, M.bitfield_lin, mip + 1)) ++mip;
+                t = advance_to_next_voxel(t, cone, px, py, pz, G.dx, G.dy, G.dz, G.ix, G.iy, G.iz, mip);
+            }
+        };
         while (true) {
             long long c0 = st ? clock64() : 0;
             // ---- A. claim hit-list entries: one thread fetches a new chunk when the group's current one is used up ----
@@ -178,11 +217,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_march_ws(const __grid_constan
                     base = __shfl_sync(0xffffffffu, base, leader);
                     const uint32_t i = base + __popc(dead & ((1u << lane) - 1));
                     if (!alive && i < mi->end[g]) {
-                        const RayEntry e = P.entries[i];
+                        const uint32_t id = resumed ? P.work_list[i] : i;
+                        const RayEntry e = P.entries[id];
                         const Mat3x4 C = P.cams[e.k];
                         ray_geom_only(C, __ldg(P.dirs + e.idx), G);          // same arithmetic as pass 1 (setup_ray)
                         G.t_exit = e.t_exit;
-                        t = e.t; ei = i;
+                        ei = id;
+                        t = resumed ? P.t_cur[id] : e.t;
                         fwx = C.c[2][0]; fwy = C.c[2][1]; fwz = C.c[2][2];
                         float sh[16];
                         const float wx = (G.dx + 1.0f) * 0.5f, wy = (G.dy + 1.0f) * 0.5f, wz = (G.dz + 1.0f) * 0.5f;
@@ -195,48 +236,26 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_march_ws(const __grid_constan
                         }
                         sh_lo[r] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         sh_hi[r] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        if (resumed) {      // a ray the split kernels brought this far: it has taken exactly resume_steps samples
+                            const float4 a = P.resume_acc4[i];
+                            acc[0 * 128 + r] = a.x; acc[1 * 128 + r] = a.y; acc[2 * 128 + r] = a.z; acc[3 * 128 + r] = a.w;
+                            acc[4 * 128 + r] = P.resume_acca[i];
+                            acc[5 * 128 + r] = __int_as_float(P.resume_steps);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) acc[j * 128 + r] = 0.f;
+                            for (int j = 0; j < 6; ++j) acc[j * 128 + r] = 0.f;
+                            ++my_rays;
+                        }
                         alive = true;
-                        ++my_rays;
+                        walked = false;
                     }
                 }
             }
-            // ---- B. up to two sample positions: one walk loop for both (generate_next_nerf_network_inputs, testbed_nerf.cu:454-467,
-            // twice): the same sequence of operations on t as two calls of if_unoccupied_advance_to_next_occupied_voxel ----
-            int n_s = 0;
-            bool exits = false;
-            float wp0x = 0.f, wp0y = 0.f, wp0z = 0.f, wp1x = 0.f, wp1y = 0.f, wp1z = 0.f;
-            float dep0 = 0.f, dep1 = 0.f, dtu0 = 0.f, dtu1 = 0.f;
+            // ---- B. up to two sample positions (rays that continue did this walk while their last MLP round was in flight) ----
             if (st) { const long long c1 = clock64(); c_refill += c1 - c0; c0 = c1; }
+            if (alive && !walked) do_walk();
+            if (!alive) { n_s = 0; exits = false; }
             if (alive) {
-                while (true) {
-                    const float px = G.ox + t * G.dx, py = G.oy + t * G.dy, pz = G.oz + t * G.dz;
-                    if (t >= MAX_DEPTH() || t > G.t_exit || !raabb_contains(M, px, py, pz)) { exits = true; break; }
-                    uint32_t mip = min(max(mip_from_pos(px, py, pz), 0u), max_mip);
-                    if (density_grid_occupied_at(px, py, pz, M.bitfield_lin, mip)) {
-                        const float dt = calc_dt(t, cone);
-                        const float wx = (px - M.aabb_min[0]) / M.aabb_diag[0];
-                        const float wy = (py - M.aabb_min[1]) / M.aabb_diag[1];
-                        const float wz = (pz - M.aabb_min[2]) / M.aabb_diag[2];
-                        // composite_kernel_nerf reads the position back from the network input (unwarp_position) and the
-                        // step from warp_dt/unwarp_dt: same arithmetic here, evaluated before the MLP instead of after
-                        const float ux = M.aabb_min[0] + wx * M.aabb_diag[0];
-                        const float uy = M.aabb_min[1] + wy * M.aabb_diag[1];
-                        const float uz = M.aabb_min[2] + wz * M.aabb_diag[2];
-                        float dep = 0.f;
-                        dep += fwx * (ux - G.ox); dep += fwy * (uy - G.oy); dep += fwz * (uz - G.oz);
-                        dep *= M.depth_scale;
-                        const float dtu = unwarp_dt(warp_dt(dt));
-                        if (n_s == 0) { wp0x = wx; wp0y = wy; wp0z = wz; dep0 = dep; dtu0 = dtu; }
-                        else { wp1x = wx; wp1y = wy; wp1z = wz; dep1 = dep; dtu1 = dtu; }
-                        t += dt;
-                        if (++n_s == 2) break;
-                        continue;
-                    }
-                    while (mip < max_mip && !density_grid_occupied_at(px, py, pz, M.bitfield_lin, mip + 1)) ++mip;
-                    t = advance_to_next_voxel(t, cone, px, py, pz, G.dx, G.dy, G.dz, G.ix, G.iy, G.iz, mip);
-                }
                 if (n_s == 0) {      // nothing left to sample: the ray is finished as it stands (accumulators of the last round)
                     P.res_rgbd[ei] = make_float4(acc[0 * 128 + r], acc[1 * 128 + r], acc[2 * 128 + r], acc[3 * 128 + r]);
                     P.res_a[ei] = acc[4 * 128 + r];
@@ -273,6 +292,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_march_ws(const __grid_constan
                 continue;
             }
             mbar_arrive(&mi->bar_a[g]);
+            // the published samples are with the MMA / epilogue warps now: walk to the next two in the meantime
+            walked = false;
+            if (alive && n_s == 2 && !exits) { do_walk(); walked = true; }
+            __syncwarp();
+            if (st) { const long long c1 = clock64(); c_walk += c1 - c0; c0 = c1; }
             mbar_wait_wd(&mi->bar_done[g], pd); pd ^= 1;
             if (alive && !stat[r]) alive = false;
             if (st) c_wait += clock64() - c0;
@@ -302,8 +326,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_march_ws(const __grid_constan
             const long long c0 = st ? clock64() : 0;
             mbar_wait_wd(&mi->bar_seq[slot], (seq / WS_RING) & 1u);
             if (st) c_wait += clock64() - c0;
-            uint32_t item;
-            {   // the entry was written before the commit was issued; the tag makes that independent of how the commit's arrive is ordered
+            uint32_t item = *reinterpret_cast<const volatile uint32_t*>(&mi->ring[slot]);
+            if ((item >> 16) != (seq & 0xffffu)) {
+                // the entry was written before the commit was issued; the tag makes reading it independent of how the commit's arrive is ordered
                 const volatile uint32_t* rp = &mi->ring[slot];
                 long long t0 = 0;
                 while (((item = *rp) >> 16) != (seq & 0xffffu)) {
@@ -329,21 +354,31 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_march_ws(const __grid_constan
             const uint32_t tm = tmem_lane + g * 128;
             float* sig = reinterpret_cast<float*>(smem + WS_SIG + g * 1024);
             if (layer == 0 || layer == 2 || layer == 3) {
-                // 64 outputs, ReLU, fp16 -> K=64 operand rows (in place for layer 3: its MMA has retired)
-#pragma unroll 1
-                for (int q = 0; q < 4; ++q) {
-                    const int s = q >> 1, hf = q & 1;
-                    uint32_t v[32];
-                    tmem_ld_32x32_x32(tm + s * 64 + hf * 32, v);
-                    tmem_ld_wait();
+                // 64 outputs, ReLU, fp16 -> K=64 operand rows (in place for layer 3: its MMA has retired).  Four chunks of 32
+                // columns, software-pipelined: chunk q+1 is on its way from TMEM while chunk q is packed and stored
+                uint32_t va[32], vb[32];
+                auto pack_store = [&](const uint32_t (&v)[32], int q) {
+                    unsigned char* dst = rowA64 + (q >> 1) * 16384 + (q & 1) * 512;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint4 o;
                         o.x = pack_relu_h2(v[8 * c + 0], v[8 * c + 1], true); o.y = pack_relu_h2(v[8 * c + 2], v[8 * c + 3], true);
                         o.z = pack_relu_h2(v[8 * c + 4], v[8 * c + 5], true); o.w = pack_relu_h2(v[8 * c + 6], v[8 * c + 7], true);
-                        *reinterpret_cast<uint4*>(rowA64 + s * 16384 + (hf * 4 + c) * 128) = o;
+                        *reinterpret_cast<uint4*>(dst + c * 128) = o;
                     }
-                }
+                };
+                tmem_ld_32x32_x32(tm, va);
+                tmem_ld_wait();
+                tmem_ld_32x32_x32(tm + 32, vb);
+                pack_store(va, 0);
+                tmem_ld_wait();
+                tmem_ld_32x32_x32(tm + 64, va);
+                pack_store(vb, 1);
+                tmem_ld_wait();
+                tmem_ld_32x32_x32(tm + 96, vb);
+                pack_store(va, 2);
+                tmem_ld_wait();
+                pack_store(vb, 3);
             } else if (layer == 1) {
                 // density layer 1: 16 outputs (row 0 = raw density); rgb input = [16 density-out | 16 SH]
                 const uint4 s0 = reinterpret_cast<const uint4*>(smem + WS_SH + g * 4096)[r];
@@ -433,7 +468,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_march_ws(const __grid_constan
         mbar_arrive_expect_tx(&mi->bar_w, 20480u);
         bulk_g2s(smem + WS_W, M.w_umma, 20480u, &mi->bar_w);
         mbar_wait_wd(&mi->bar_w, 0);
-        const uint32_t wbase = smem_u32(smem + WS_W);
+        const uint32_t wbase = smem_u32(smem + WS_W), abase = smem_u32(smem + WS_A);
         // per-group state packed into registers (dynamic indexing of local arrays would go through local memory):
         // layers: 4 bits per group = next layer to issue; pa: parity bit per group of bar_a; gone: bit per group
         uint32_t layers = 0, pa = 0, gone = 0;
@@ -444,7 +479,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_march_ws(const __grid_constan
         long long c_issue = 0;
         while (n_active) {
             bool any = false;
-#pragma unroll
+#pragma unroll 1
             for (int g = 0; g < WS_NG; ++g) {
                 if ((gone >> g) & 1u) continue;
                 if (!mbar_test(&mi->bar_a[g], (pa >> g) & 1u)) continue;
@@ -456,19 +491,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_march_ws(const __grid_constan
                 const long long ci = STATS ? clock64() : 0;
                 const uint32_t slot = seq % WS_RING;
                 *reinterpret_cast<volatile uint32_t*>(&mi->ring[slot]) = ((seq & 0xffffu) << 16) | (L << 8) | (uint32_t)g;
-                const int K = (L == 0 || L == 2) ? 32 : 64, N = (L == 1 || L == 4) ? 16 : 64;
-                const uint32_t w_off = L == 0 ? (uint32_t)W_D0 : L == 1 ? (uint32_t)W_D1 : L == 2 ? (uint32_t)W_C0 : L == 3 ? (uint32_t)W_C1 : (uint32_t)W_C2;
-                const uint32_t idesc = N == 16 ? umma_idesc_f16(128, 16, 0) : umma_idesc_f16(128, 64, 0);
-                const uint32_t sbo = (uint32_t)(K / 8) * 128;
-                const uint32_t a_addr = smem_u32(smem + WS_A + g * 32768), b_addr = wbase + w_off;
-#pragma unroll 1
-                for (int s = 0; s < 2; ++s) {
-#pragma unroll 1
-                    for (int kk = 0; kk < K / 16; ++kk) {
-                        const uint64_t da = umma_desc_noswz(a_addr + s * 16384 + kk * 256, 128, sbo);
-                        const uint64_t db = umma_desc_noswz(b_addr + kk * 256, 128, sbo);
-                        umma_f16_ss(tmem_base + g * 128 + s * 64, da, db, idesc, kk > 0);
-                    }
+                // descriptor low words: (address >> 4) | LBO (128 B >> 4) << 16; all operand addresses are below 256 KB
+                const uint32_t a_lo = (abase >> 4) + (uint32_t)g * 2048u + (8u << 16), w_lo = (wbase >> 4) + (8u << 16);
+                const uint32_t td = tmem_base + (uint32_t)g * 128u;
+                switch (L) {
+                    case 0: issue_layer_ws<32, 64>(a_lo, w_lo + (W_D0 >> 4), td); break;
+                    case 1: issue_layer_ws<64, 16>(a_lo, w_lo + (W_D1 >> 4), td); break;
+                    case 2: issue_layer_ws<32, 64>(a_lo, w_lo + (W_C0 >> 4), td); break;
+                    case 3: issue_layer_ws<64, 64>(a_lo, w_lo + (W_C1 >> 4), td); break;
+                    default: issue_layer_ws<64, 16>(a_lo, w_lo + (W_C2 >> 4), td); break;
                 }
                 tc_commit(&mi->bar_seq[slot]);
                 if (STATS) c_issue += clock64() - ci;

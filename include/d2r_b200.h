@@ -186,6 +186,25 @@ int d2r_score(const float* img_embeds_dev, const float* txt_embeds_dev, int K, i
               float logit_scale_exp, int n_goal, float* scores_out_dev, float* logits_out_dev,
               void* stream);
 
+/* ---- pre-render physics filter ------------------------------------------------
+ * The per-pose part of `unsupcol_check` (vision_3d/physics_utils.py:305-372) for all N poses of the grid in one launch: in
+ * collision -> invalid; moved `unsup_thresh` down along gravity the object must touch a support unless the pose lies below
+ * the table plane; lowered, it must still touch one when pushed `p_dist` along +-x and +-y.  The collision primitive is an
+ * occupancy overlap: fg_points_world_dev [n_pts,4] float = occupied cell centres of the movable object's density grid (world
+ * frame, initial pose; w unused), moved by rel_3x4_dev [N,12] = pose . init_pose^-1, against the occupancy bitfield of `bg`.
+ * pose_z_dev [N] = z of the candidate pose; valid_in_dev / valid_out_dev [N] uint8.                                   */
+typedef struct {
+    float dataset_scale;       /* world -> NGP: p * scale + offset, xyz <- yzx (nerf_loader.h:148-151) */
+    float dataset_offset[3];
+    float scene_centre_z;      /* task_model.scene_model.scene_centre[2] */
+    float unsup_thresh;        /* 0.02 */
+    float p_dist;              /* 0.04 */
+    int32_t stability_check;
+} d2r_phys_cfg;
+int d2r_phys_check(const d2r_model* bg, const float* fg_points_world_dev, int n_pts, const float* rel_3x4_dev,
+                   const float* pose_z_dev, const uint8_t* valid_in_dev, int N, const d2r_phys_cfg* cfg,
+                   uint8_t* valid_out_dev, void* stream);
+
 /* ---- building block exported for tests: the tcgen05 GEMM every ViT contraction runs on ----------
  * out = A[M,K] . B[N,K]^T (+bias[N]); A, B fp16 K-major device pointers with leading dimensions
  * lda/ldb (elements); K % 64 == 0, N % 64 == 0.  mode: 0 fp16 out, 1 fp16 quick-GELU out,

@@ -111,3 +111,44 @@ def test_use_cache_renders_and_aliases(tmp_path):
         clip_scoring.optimise_pose_grid(r, None, [0], tm, d, **dict(kw, phys_check=lambda p, t, v: torch.zeros_like(v)))
     best, _, ones = clip_scoring.optimise_pose_grid(r, None, [0], tm, d, physics_only=True, **kw)
     assert best.shape == (4, 4) and torch.all(ones == 1)
+
+
+def test_full_shopping_grid_streams_through_a_few_gb(tmp_path):
+    """The reference's own shopping pose grid (configs/shopping_demo.json:28: sample_res [100,100,7,1,1,1] = 70 000 poses) at
+    800x800 through optimise_pose_grid on one GPU: render -> preprocess -> encode -> score per chunk, so only O(chunk) frames (256 here)
+    exist at any time (all 70 000 frames would be 134 GB).  Device memory in use stays below 8 GB; scores come back for every
+    pose, and a pose's score does not depend on the chunking (checked against a separate run of a slice of the grid)."""
+    import time
+
+    import torch
+    from dream2real_b200 import clip_scoring, synth
+    from dream2real_b200.clip import make_hf_clip
+    from dream2real_b200.reconstruction.combined_rendering import renderer
+    d = str(tmp_path)
+    scene = synth.make_scene("shopping", d, log2_hashmap_size=19, seed=1234)
+    tm = synth.SyntheticTaskModel(scene, "goal", ["norm"], torch.device("cuda"))
+    model = make_hf_clip("ViT-B/32", seed=1234, vocab_size=49408)
+    ids = torch.randint(3, 40000, (2, 12), generator=torch.Generator().manual_seed(1234))
+    ids[:, -1] = 2
+    sample_res = [100, 100, 7, 1, 1, 1]
+    r = renderer(d, tm, resolution=800, max_candidates_per_launch=256)
+    kw = dict(phys_check=synth.all_valid_phys_check, scene_type=3, smoothing=False, clip_model=model, text_inputs={"input_ids": ids},
+              save_renders=False, clip_batch_size=256)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    best, poses, scores = clip_scoring.optimise_pose_grid(r, tm.depths[:1], [0], tm, d, sample_res=sample_res, **kw)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    free, total = torch.cuda.mem_get_info()
+    used_gb = (total - free) / 2 ** 30
+    print(f"70 000 poses at 800x800: {dt:.1f} s wall ({70000 / dt:.0f} candidates/s incl. CLIP load + text), {used_gb:.2f} GB of device memory in use")
+    assert poses.shape == (70000, 16) and scores.shape == (70000,) and bool((scores != 0).all()) and bool(torch.isfinite(scores).all())
+    assert used_gb < 8.0
+    assert os.path.exists(os.path.join(d, "best_render.png"))
+    # chunking does not show: the first 3 x-slabs (2100 poses, z fastest) scored on their own, in chunks of 300
+    r2 = renderer(d, tm, resolution=800, max_candidates_per_launch=300)
+    _, _, s2 = clip_scoring.optimise_pose_grid(r2, tm.depths[:1], [0], tm, d, sample_res=[3, 100, 7, 1, 1, 1], **dict(kw, clip_batch_size=300))
+    # the 3-slab grid spans the same x range with 3 samples: its first slab (x = lower bound) equals the big grid's first slab
+    first = clip_scoring.sample_poses_grid(tm, [3, 100, 7, 1, 1, 1], scene_type=3)[:700]
+    assert torch.equal(first, poses[:700])
+    assert torch.allclose(s2[:700], scores[:700], rtol=1e-6, atol=1e-7)

@@ -58,3 +58,39 @@ def test_opaque_background_blend(fox, golden_dir):
     assert np.allclose(shade[..., 3], 1.0, atol=1e-6) and np.allclose(g["Shade"][0][..., 3], 1.0, atol=1e-6)
     e = np.abs(shade - g["Shade"][0])
     assert np.percentile(e, 99.9) < 1e-3 and e.mean() < 1e-4
+
+
+def test_synthetic_scene_conditioning(tmp_path, golden_dir):
+    """How much latitude the reference's OWN arithmetic leaves on the synthetic bench scenes (random +-0.5 hash tables behind
+    random MLPs with a gain-4 colour head): the oracle with fp16-accumulating wmma fragments (what the reference runs) against
+    the oracle with an exact dot product differs by more than 1e-3 on a fraction of a per cent of the pixels, and so does real
+    pyngp (tests/golden/synth_shopping.npz) against either.  tests/test_bench_config_gpu.py bounds the CUDA kernels by this
+    spread; the trained snapshot (fox) above is held to 1e-3."""
+    from dream2real_b200 import synth
+    g = np.load(os.path.join(golden_dir, "synth_shopping.npz"))
+    res = 336
+    d = str(tmp_path)
+    synth.make_scene("shopping", d, log2_hashmap_size=19, seed=1234)
+    fg = ingp.load_snapshot(os.path.join(d, "fg_base.ingp"))
+    bits, _ = O.build_bitfield(fg.density_grid, fg.max_cascade)
+    vs = O.view_setup(fg, 0, res, res)
+    dirs = O.camera_plane_dirs(vs)
+    box = O.occupied_box(bits, fg.max_cascade)
+    y0, y1, x0, x1 = [int(v) for v in g[f"rect_{res}_0"]]
+    out = {}
+    for acc in ("fp16_k16", "fp32"):
+        st = O.RenderStats()
+        sh, _ = O.render(fg, bits, vs, g["cams"][0][:3], both=True, background_color=[0, 0, 0, 0], plane_dirs=dirs, cull_box=box, accum=acc, stats=st)
+        assert not sh[:y0].any() and not sh[y1:].any() and not sh[:, :x0].any() and not sh[:, x1:].any()
+        out[acc] = sh[y0:y1, x0:x1]
+        # the oracle takes the reference's samples: step totals agree to 3 % (Cost counts one extra step per exhausted ray)
+        assert abs(st.n_samples - float(g[f"cost_{res}_0"].sum())) / float(g[f"cost_{res}_0"].sum()) < 0.03
+    ref = g[f"shade_{res}_0"]
+    spread = np.abs(out["fp16_k16"] - out["fp32"]).max(-1)
+    e16, e32 = np.abs(out["fp16_k16"] - ref).max(-1), np.abs(out["fp32"] - ref).max(-1)
+    print(f"fp16-accumulate vs fp32-accumulate oracle: >1e-3 on {int((spread > 1e-3).sum())} of {spread.size} px, max {spread.max():.4f}; "
+          f"pyngp vs oracle fp16: {int((e16 > 1e-3).sum())} px, vs oracle fp32: {int((e32 > 1e-3).sum())} px")
+    n = spread.size
+    assert 5 <= (spread > 1e-3).sum() < 0.02 * n            # the reference's own accumulate type moves pixels by more than the tolerance here
+    assert (e16 > 1e-3).sum() < 0.02 * n and (e32 > 1e-3).sum() < 0.02 * n
+    assert np.percentile(e16, 95) < 1e-3 and e16.mean() < 5e-4
