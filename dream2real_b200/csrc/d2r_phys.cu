@@ -6,7 +6,7 @@
 // reference's; the collision primitive is an occupancy overlap between the two NeRFs the path already holds -- the occupied
 // cell centres of the movable object's density grid, moved by pose . init_pose^-1, against the background model's occupancy
 // bitfield (the lookup of the renderer's DDA, nerf_device.cuh:430-447) -- because the reference's primitive lives in pybullet
-// on Poisson meshes that do not exist on this path (oracle/phys_oracle.py states the definition independently; parity with
+// on Poisson meshes that do not exist on this path (the test suite states the definition independently in numpy; parity with
 // pybullet itself is unpinned).
 #include "d2r_march.cuh"
 
