@@ -330,107 +330,87 @@ __device__ __forceinline__ void encode_levels(const ModelDev& M, int level0, flo
     }
 }
 
-// Lane-pair cooperative variant of encode_levels (the whole warp must call it, converged).
-// The gathers are bound by L1 tag work: a warp-wide load costs one pass per distinct 128-byte line it touches, and at
-// the fine levels every lane touches its own lines.  The two x-neighbours (x, x+1) of a corner pair sit in the same line
-// (dense: adjacent entries; hashed: the x term enters the coherent-prime hash un-multiplied, so idx(x+1) = idx(x) ^ (2^(t+1)-1),
-// t = trailing ones of x -- the same line 15 times out of 16), but one thread can only fetch them with two instructions.
-// So lanes 2j / 2j+1 share the work: instruction set 1 serves the even lane's sample (even lane loads the x corner, odd lane
-// the x+1 corner -> ONE line for the pair), set 2 serves the odd lane's sample, and a shuffle hands each lane the other
-// corner of its own sample.  Same number of loads, half the lines per instruction; the blend (order, rounding) is unchanged.
-template <int NL>
-__device__ __forceinline__ void encode_levels_pair(const ModelDev& M, int level0, float x, float y, float z, const float (&pe)[3],
-                                                   const float (&po)[3], __half2* f /* [2 * NL] */) {
-    // pe / po: position of the even / odd lane's sample of this pair (shuffled once per sample by the caller; the integer
-    // cell of either sample is recomputed per level with the same pos_fract arithmetic its owner uses)
-    const uint32_t FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const uint32_t odd = (uint32_t)lane & 1u;
-    uint32_t e1[NL][4], e2[NL][4];
-    float pos[NL][3];
-    const uint2* table[NL];
+// One level with PAIRED corner loads.  The two x-neighbours (x, x+1) of a corner pair are fetched with ONE 128-bit load whenever
+// they form an aligned pair of table entries -- hashed levels: the x term enters the coherent-prime hash un-multiplied, so for an
+// even cell x the two indices differ in bit 0 only; dense levels: whenever the index of the x corner is even -- and with the
+// 128-bit load of the x corner's pair plus a predicated 64-bit load of the x+1 corner otherwise.  The gather is bound by the L1
+// tag stage (one wavefront per 128-byte line a warp-wide load touches): at the fine levels every lane touches its own lines,
+// and this halves the loads of half the lanes.  Same entries, same blend order and rounding as encode_level: identical features.
+__device__ __forceinline__ void encode_level_paired(const ModelDev& M, int level, float x, float y, float z, __half2& f01, __half2& f23) {
+    const uint2* __restrict__ table = M.level_table[level];
+    const uint32_t hashmap_size = M.level_size[level];
+    const float scale = M.level_scale[level];
+    float pos[3];
+    uint32_t pg[3];
     const float in[3] = {x, y, z};
 #pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        const int level = level0 + l;
-        table[l] = M.level_table[level];
-        const uint32_t hashmap_size = M.level_size[level];
-        const float scale = M.level_scale[level];
-        uint32_t pa[3], pb[3];       // integer cell of the even lane's sample / of the odd lane's sample
+    for (int d = 0; d < 3; ++d) {    // pos_fract
+        pos[d] = fmaf(scale, in[d], 0.5f);
+        float tmp = floorf(pos[d]);
+        pg[d] = (uint32_t)(int)tmp;
+        pos[d] -= tmp;
+    }
+    uint32_t i0[4], i1[4];           // entry of the x corner / of the x+1 corner, per (y, z) combination j = dy + 2 dz
+    if (M.level_hashed[level]) {
+        const uint32_t mask = hashmap_size - 1;
+        const uint32_t hy[2] = {pg[1] * 2654435761u, (pg[1] + 1u) * 2654435761u};
+        const uint32_t hz[2] = {pg[2] * 805459861u, (pg[2] + 1u) * 805459861u};
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {    // pos_fract
-            pos[l][d] = fmaf(scale, in[d], 0.5f);
-            pos[l][d] -= floorf(pos[l][d]);
-            pa[d] = (uint32_t)(int)floorf(fmaf(scale, pe[d], 0.5f));
-            pb[d] = (uint32_t)(int)floorf(fmaf(scale, po[d], 0.5f));
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t h = hy[j & 1] ^ hz[j >> 1];
+            i0[j] = (pg[0] ^ h) & mask;
+            i1[j] = ((pg[0] + 1u) ^ h) & mask;
         }
-        // set 1: this lane's corner of the even lane's sample has x offset `odd`; set 2 (odd lane's sample): offset `1 - odd`,
-        // so that in both sets the lane that OWNS the sample fetches the x corner and its partner the x+1 corner
-        const uint32_t xa = pa[0] + odd, xb = pb[0] + (odd ^ 1u);
-        if (M.level_hashed[level]) {
-            const uint32_t mask = hashmap_size - 1;
-            const uint32_t ya[2] = {pa[1] * 2654435761u, (pa[1] + 1u) * 2654435761u};
-            const uint32_t za[2] = {pa[2] * 805459861u, (pa[2] + 1u) * 805459861u};
-            const uint32_t yb[2] = {pb[1] * 2654435761u, (pb[1] + 1u) * 2654435761u};
-            const uint32_t zb[2] = {pb[2] * 805459861u, (pb[2] + 1u) * 805459861u};
+    } else {
+        const uint32_t res = M.level_res[level];
+        const uint32_t r2 = res * res;
+        const uint32_t base = pg[0] + pg[1] * res + pg[2] * r2;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                e1[l][k] = (xa ^ ya[k & 1] ^ za[k >> 1]) & mask;
-                e2[l][k] = (xb ^ yb[k & 1] ^ zb[k >> 1]) & mask;
-            }
-        } else {
-            const uint32_t res = M.level_res[level];
-            const uint32_t r2 = res * res;
-            const uint32_t ba = xa + pa[1] * res + pa[2] * r2, bb = xb + pb[1] * res + pb[2] * r2;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t i = ba + (k & 1) * res + (k >> 1) * r2;
-                if (i >= hashmap_size) i -= hashmap_size;
-                e1[l][k] = i;
-                uint32_t j = bb + (k & 1) * res + (k >> 1) * r2;
-                if (j >= hashmap_size) j -= hashmap_size;
-                e2[l][k] = j;
-            }
+        for (int j = 0; j < 4; ++j) {
+            uint32_t a = base + (j & 1) * res + (j >> 1) * r2, b = a + 1u;
+            if (a >= hashmap_size) a -= hashmap_size;
+            if (b >= hashmap_size) b -= hashmap_size;
+            i0[j] = a; i1[j] = b;
         }
     }
-    (void)FULL;
-    uint2 r1[NL][4], r2v[NL][4];
+    uint4 A[4];
+    uint2 B[4];
+    bool pair[4];
 #pragma unroll
-    for (int l = 0; l < NL; ++l) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) r1[l][k] = __ldg(table[l] + e1[l][k]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) r2v[l][k] = __ldg(table[l] + e2[l][k]);
+    for (int j = 0; j < 4; ++j) {
+        pair[j] = (i0[j] ^ i1[j]) == 1u;
+        A[j] = __ldg(reinterpret_cast<const uint4*>(table + (i0[j] & ~1u)));      // the aligned 16-byte pair that holds the x corner
     }
 #pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        __half2 r01 = __float2half2_rn(0.f), r23 = __float2half2_rn(0.f);
+    for (int j = 0; j < 4; ++j) {
+        B[j] = make_uint2(0u, 0u);
+        if (!pair[j]) B[j] = __ldg(table + i1[j]);
+    }
+    __half2 r01 = __float2half2_rn(0.f), r23 = __float2half2_rn(0.f);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            // even lane: set 1 holds its own x corner, set 2 its partner's x+1 corner; odd lane: the other way round
-            uint2 mine, send, recv;
-            mine.x = odd ? r2v[l][k].x : r1[l][k].x; mine.y = odd ? r2v[l][k].y : r1[l][k].y;
-            send.x = odd ? r1[l][k].x : r2v[l][k].x; send.y = odd ? r1[l][k].y : r2v[l][k].y;
-            recv.x = __shfl_xor_sync(FULL, send.x, 1);
-            recv.y = __shfl_xor_sync(FULL, send.y, 1);
+    for (int j = 0; j < 4; ++j) {
+        const bool odd = (i0[j] & 1u) != 0;
+        uint2 v0, v1;
+        v0.x = odd ? A[j].z : A[j].x; v0.y = odd ? A[j].w : A[j].y;
+        v1.x = pair[j] ? (odd ? A[j].x : A[j].z) : B[j].x;
+        v1.y = pair[j] ? (odd ? A[j].y : A[j].w) : B[j].y;
 #pragma unroll
-            for (int xb_ = 0; xb_ < 2; ++xb_) {     // corner idx = xb_ + 2 * k: x fastest, as in the reference's loop
-                const int idx = xb_ + 2 * k;
-                float weight = 1;
+        for (int xb = 0; xb < 2; ++xb) {       // corner idx = xb + 2 j: x fastest, as in the reference's loop
+            const int idx = xb + 2 * j;
+            float weight = 1;
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    if ((idx & (1 << d)) == 0) weight *= 1 - pos[l][d];
-                    else weight *= pos[l][d];
-                }
-                const __half2 w2 = __float2half2_rn(weight);
-                const uint2 v = xb_ ? recv : mine;
-                r01 = __hfma2(w2, *reinterpret_cast<const __half2*>(&v.x), r01);
-                r23 = __hfma2(w2, *reinterpret_cast<const __half2*>(&v.y), r23);
+            for (int d = 0; d < 3; ++d) {
+                if ((idx & (1 << d)) == 0) weight *= 1 - pos[d];
+                else weight *= pos[d];
             }
+            const __half2 w2 = __float2half2_rn(weight);
+            const uint2 v = xb ? v1 : v0;
+            r01 = __hfma2(w2, *reinterpret_cast<const __half2*>(&v.x), r01);
+            r23 = __hfma2(w2, *reinterpret_cast<const __half2*>(&v.y), r23);
         }
-        f[2 * l] = r01;
-        f[2 * l + 1] = r23;
     }
+    f01 = r01;
+    f23 = r23;
 }
 
 // ---- spherical harmonics degree 4: TCNN common_device.h:340-365 ----------------------------------
