@@ -311,7 +311,6 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
     // D2R_MARCH=ws | split force one kernel for every launch (split: its tail still goes through k_march_ws).
     static const int mode = []() { const char* e = getenv("D2R_MARCH"); return !e || !*e ? 0 : strcmp(e, "ws") == 0 ? 1 : strcmp(e, "split") == 0 ? 2 : 0; }();
     static const int split_rounds = []() { const char* e = getenv("D2R_SPLIT_ROUNDS"); const int v = e ? atoi(e) : 16; return v >= 1 && v <= 256 ? v : 16; }();
-    static const bool gather_paired = []() { const char* e = getenv("D2R_GATHER_PAIRED"); return e && atoi(e) != 0; }();
     constexpr size_t SPLIT_MIN_RAYS = 1u << 20;
     const bool use_split = !cost_out && (mode == 2 || (mode == 0 && need >= SPLIT_MIN_RAYS));
     P.work_list = nullptr; P.work_count = nullptr; P.t_cur = nullptr; P.resume_acc4 = nullptr; P.resume_acca = nullptr; P.resume_steps = 0;
@@ -366,8 +365,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
             Q.cnt_in = s.sp_cnt + r; Q.cnt_out = s.sp_cnt + r + 1;
             Q.live_in = s.sp_live[r & 1]; Q.live_out = s.sp_live[(r + 1) & 1];
             Q.acc4_in = s.sp_acc4[r & 1]; Q.acca_in = s.sp_acca[r & 1]; Q.acc4_out = s.sp_acc4[(r + 1) & 1]; Q.acca_out = s.sp_acca[(r + 1) & 1];
-            if (gather_paired) k_gather_round<true><<<s.n_sm * 8, 128, 0, stream>>>(P, Q);
-            else k_gather_round<false><<<s.n_sm * 7, 128, 0, stream>>>(P, Q);
+            k_gather_round<<<s.n_sm * 7, 128, 0, stream>>>(P, Q);
             k_mlp_round<<<s.n_sm * 3, TC_THREADS, T2_TOTAL, stream>>>(P, Q);
             count_launch(2);
         }

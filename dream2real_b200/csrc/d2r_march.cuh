@@ -330,89 +330,6 @@ __device__ __forceinline__ void encode_levels(const ModelDev& M, int level0, flo
     }
 }
 
-// One level with PAIRED corner loads.  The two x-neighbours (x, x+1) of a corner pair are fetched with ONE 128-bit load whenever
-// they form an aligned pair of table entries -- hashed levels: the x term enters the coherent-prime hash un-multiplied, so for an
-// even cell x the two indices differ in bit 0 only; dense levels: whenever the index of the x corner is even -- and with the
-// 128-bit load of the x corner's pair plus a predicated 64-bit load of the x+1 corner otherwise.  The gather is bound by the L1
-// tag stage (one wavefront per 128-byte line a warp-wide load touches): at the fine levels every lane touches its own lines,
-// and this halves the loads of half the lanes.  Same entries, same blend order and rounding as encode_level: identical features.
-__device__ __forceinline__ void encode_level_paired(const ModelDev& M, int level, float x, float y, float z, __half2& f01, __half2& f23) {
-    const uint2* __restrict__ table = M.level_table[level];
-    const uint32_t hashmap_size = M.level_size[level];
-    const float scale = M.level_scale[level];
-    float pos[3];
-    uint32_t pg[3];
-    const float in[3] = {x, y, z};
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {    // pos_fract
-        pos[d] = fmaf(scale, in[d], 0.5f);
-        float tmp = floorf(pos[d]);
-        pg[d] = (uint32_t)(int)tmp;
-        pos[d] -= tmp;
-    }
-    uint32_t i0[4], i1[4];           // entry of the x corner / of the x+1 corner, per (y, z) combination j = dy + 2 dz
-    if (M.level_hashed[level]) {
-        const uint32_t mask = hashmap_size - 1;
-        const uint32_t hy[2] = {pg[1] * 2654435761u, (pg[1] + 1u) * 2654435761u};
-        const uint32_t hz[2] = {pg[2] * 805459861u, (pg[2] + 1u) * 805459861u};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t h = hy[j & 1] ^ hz[j >> 1];
-            i0[j] = (pg[0] ^ h) & mask;
-            i1[j] = ((pg[0] + 1u) ^ h) & mask;
-        }
-    } else {
-        const uint32_t res = M.level_res[level];
-        const uint32_t r2 = res * res;
-        const uint32_t base = pg[0] + pg[1] * res + pg[2] * r2;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint32_t a = base + (j & 1) * res + (j >> 1) * r2, b = a + 1u;
-            if (a >= hashmap_size) a -= hashmap_size;
-            if (b >= hashmap_size) b -= hashmap_size;
-            i0[j] = a; i1[j] = b;
-        }
-    }
-    uint4 A[4];
-    uint2 B[4];
-    bool pair[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        pair[j] = (i0[j] ^ i1[j]) == 1u;
-        A[j] = __ldg(reinterpret_cast<const uint4*>(table + (i0[j] & ~1u)));      // the aligned 16-byte pair that holds the x corner
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        B[j] = make_uint2(0u, 0u);
-        if (!pair[j]) B[j] = __ldg(table + i1[j]);
-    }
-    __half2 r01 = __float2half2_rn(0.f), r23 = __float2half2_rn(0.f);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const bool odd = (i0[j] & 1u) != 0;
-        uint2 v0, v1;
-        v0.x = odd ? A[j].z : A[j].x; v0.y = odd ? A[j].w : A[j].y;
-        v1.x = pair[j] ? (odd ? A[j].x : A[j].z) : B[j].x;
-        v1.y = pair[j] ? (odd ? A[j].y : A[j].w) : B[j].y;
-#pragma unroll
-        for (int xb = 0; xb < 2; ++xb) {       // corner idx = xb + 2 j: x fastest, as in the reference's loop
-            const int idx = xb + 2 * j;
-            float weight = 1;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                if ((idx & (1 << d)) == 0) weight *= 1 - pos[d];
-                else weight *= pos[d];
-            }
-            const __half2 w2 = __float2half2_rn(weight);
-            const uint2 v = xb ? v1 : v0;
-            r01 = __hfma2(w2, *reinterpret_cast<const __half2*>(&v.x), r01);
-            r23 = __hfma2(w2, *reinterpret_cast<const __half2*>(&v.y), r23);
-        }
-    }
-    f01 = r01;
-    f23 = r23;
-}
-
 // ---- spherical harmonics degree 4: TCNN common_device.h:340-365 ----------------------------------
 __device__ __forceinline__ void sh_enc4(float x, float y, float z, float* o) {
     float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;

@@ -37,9 +37,7 @@ struct SplitParams {
 
 constexpr int SPLIT_TILE_BYTES = 128 * 32 * 2;
 
-// PAIRED: encode_level_paired (one level at a time, x-neighbour pairs in one 128-bit load) instead of encode_levels<2>
-template <bool PAIRED>
-__global__ void __launch_bounds__(128, PAIRED ? 8 : 7) k_gather_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
+__global__ void __launch_bounds__(128, 7) k_gather_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
     const ModelDev& M = P.M;
     const int tid = threadIdx.x;
     if (*P.n_entries > Q.cap) return;
@@ -117,12 +115,7 @@ __global__ void __launch_bounds__(128, PAIRED ? 8 : 7) k_gather_round(const __gr
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     __half2 f[4];
-                    if (PAIRED) {
-                        encode_level_paired(M, 2 * c, sx, sy, sz, f[0], f[1]);
-                        encode_level_paired(M, 2 * c + 1, sx, sy, sz, f[2], f[3]);
-                    } else {
-                        encode_levels<2>(M, 2 * c, sx, sy, sz, f);
-                    }
+                    encode_levels<2>(M, 2 * c, sx, sy, sz, f);
                     uint4 v;
                     v.x = *reinterpret_cast<uint32_t*>(&f[0]); v.y = *reinterpret_cast<uint32_t*>(&f[1]);
                     v.z = *reinterpret_cast<uint32_t*>(&f[2]); v.w = *reinterpret_cast<uint32_t*>(&f[3]);
