@@ -122,6 +122,19 @@ def test_clip_vit_l14_336_vs_hf():
     _clip_parity(make_hf_clip("ViT-L/14-336", seed=11, vocab_size=1000), K=2, seed=3, tol_cos=1e-4, tol_logit_rel=2e-3)
 
 
+def test_clip_trained_checkpoint_when_present():
+    """With the real `openai/clip-vit-large-patch14-336` checkpoint on disk (D2R_CLIP_PATH, what clip_scoring.py:150 downloads)
+    the same parity run uses TRAINED weights -- their activation ranges are what the fp16 intermediates (h, qkv, m) must hold.
+    There is no network on the test boxes, so without the variable this is skipped, not passed."""
+    import os
+    path = os.environ.get("D2R_CLIP_PATH")
+    if not path or not os.path.isdir(path):
+        pytest.skip("D2R_CLIP_PATH does not point at a local copy of the CLIP checkpoint")
+    from transformers import CLIPModel
+    model = CLIPModel.from_pretrained(path, attn_implementation="eager").eval()
+    _clip_parity(model, K=4, seed=5, tol_cos=1e-4, tol_logit_rel=2e-3)
+
+
 @pytest.fixture(scope="module")
 def scene(tmp_path_factory):
     from dream2real_b200 import synth
