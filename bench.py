@@ -75,13 +75,13 @@ def parse():
 
 def pose_grid(scene, n, grid=None, rank=0, world=1, sharded=False):
     """Candidate poses of this rank: sample_poses_grid(grid) for the scene type (x slowest ... z-rotation fastest).
-    sharded: the contiguous shard `rank` of the full grid (clip_scoring.shard_bounds); else the first n poses (repeated if the
+    sharded: this rank's shard of the full grid (clip_scoring.shard_indices, strided); else the first n poses (repeated if the
     grid is smaller), which the caller offsets per rank."""
     import types
 
     import torch
 
-    from dream2real_b200.clip_scoring import shard_bounds
+    from dream2real_b200.clip_scoring import shard_indices
     from dream2real_b200.vision_3d.obj_pose_opt import sample_poses_grid
     if grid is None:
         g = int(np.ceil(np.sqrt(n)))
@@ -89,8 +89,7 @@ def pose_grid(scene, n, grid=None, rank=0, world=1, sharded=False):
     tm = types.SimpleNamespace(scene_model=types.SimpleNamespace(scene_centre=torch.tensor(scene["scene_centre"]), device=torch.device("cpu")))
     p = sample_poses_grid(tm, grid, scene_type=scene["scene_type"])
     if sharded:
-        lo, hi = shard_bounds(p.shape[0], world, rank)
-        p = p[lo:hi]
+        p = p[shard_indices(p.shape[0], world, rank)]      # strided: what optimise_pose_grid does (balanced ranks)
         n = min(n, p.shape[0]) if p.shape[0] else n
     reps = int(np.ceil(n / max(1, p.shape[0])))
     return p.repeat(reps, 1)[:n].reshape(-1, 4, 4).numpy().astype(np.float64), grid

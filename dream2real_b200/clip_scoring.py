@@ -54,14 +54,30 @@ def shard_bounds(n, world_size, rank):
     return lo, min(lo + per, n)
 
 
-def gather_scores(local_scores, n_total, world_size, rank, group=None):
-    """ONE all-gather of the per-rank score shard (padded to ceil(n/R)) -> full [n_total] vector on every rank."""
+def shard_indices(n, world_size, rank, mode="strided"):
+    """Indices of the candidates rank `rank` scores.  "contiguous": the block [lo, hi) of shard_bounds (SURVEY.md 8(e));
+    "strided" (default): rank, rank + R, rank + 2R, ... -- a pose grid is ordered x slowest, so contiguous blocks are x-slabs
+    whose objects sit at different distances from the camera and cost different amounts (the shelf grid sharded 8 ways: the
+    slowest slab took 1.6x the mean); interleaving gives every rank the same mix."""
+    if mode == "contiguous":
+        lo, hi = shard_bounds(n, world_size, rank)
+        return torch.arange(lo, hi)
+    if mode != "strided":
+        raise ValueError("shard mode must be 'strided' or 'contiguous'")
+    return torch.arange(rank, n, world_size)
+
+
+def gather_scores(local_scores, n_total, world_size, rank, group=None, mode="contiguous"):
+    """ONE all-gather of the per-rank score shard (padded to ceil(n/R)) -> full [n_total] vector on every rank, in the
+    candidates' original order for either sharding mode."""
     import torch.distributed as dist
     per = (n_total + world_size - 1) // world_size
     buf = torch.zeros(per, dtype=torch.float32, device=local_scores.device)
     buf[: local_scores.numel()] = local_scores
     out = torch.empty(per * world_size, dtype=torch.float32, device=local_scores.device)
     dist.all_gather_into_tensor(out, buf, group=group)
+    if mode == "strided":      # out[r, j] is candidate j * R + r
+        out = out.view(world_size, per).t().reshape(-1)
     return out[:n_total]
 
 
@@ -93,12 +109,14 @@ def optimise_pose_grid(renderer,
                        save_renders=True,
                        show_best=False,
                        clip_batch_size=512,
-                       multi_view="mean"):
+                       multi_view="mean",
+                       shard="strided"):
     """Reference signature and return value (clip_scoring.py:71-235).  Keyword-only extras: clip_model / clip_processor /
     text_inputs (inject a loaded CLIP instead of downloading one), save_renders, show_best, clip_batch_size, and
     multi_view: with more than one entry in render_cam_pose_idx the reference indexes K*L renders as if they were K
     (clip_scoring.py:205-206 -- it only ever runs with one view); here the L per-view scores of a pose are averaged
-    ("mean") or the best view is taken ("max")."""
+    ("mean") or the best view is taken ("max"); shard: how the valid poses are split over the ranks of an initialised
+    torch.distributed group ("strided" balances the ranks, "contiguous" is the block split; shard_indices)."""
     if use_vis_pcds:
         raise NotImplementedError("the point-cloud ablation renderer is not on the accelerated path")
     if multi_view not in ("mean", "max"):
@@ -149,7 +167,7 @@ def optimise_pose_grid(renderer,
         print('Rendering images from ngp...')
         render_poses_ngp = accio2ngp.converter(render_poses)
         valid_poses_ngp = accio2ngp.converter(valid_poses.cpu().numpy().reshape(-1, 4, 4))
-        lo, hi = shard_bounds(valid_poses_ngp.shape[0], world, rank)
+        mine = shard_indices(valid_poses_ngp.shape[0], world, rank, shard).numpy()
         stream_args = (valid_poses_ngp, render_poses_ngp)
 
     print('Evaluating rendered images using CLIP...')
@@ -176,13 +194,13 @@ def optimise_pose_grid(renderer,
 
     with torch.no_grad():
         vision = _vision_for(clip_model, device.index, clip_batch_size)
-        if stream_args is not None and hi > lo:
+        if stream_args is not None and len(mine) > 0:
             # render -> preprocess -> encode -> score per chunk: only [n_views, K] scores outlive a chunk (the reference renders
             # everything first, clip_scoring.py:120-147; at 800x800 its 70 000-pose shopping grid would be 134 GB of frames)
             valid_poses_ngp, render_poses_ngp = stream_args
-            local = torch.empty((n_views, hi - lo), dtype=torch.float32, device=device)
+            local = torch.empty((n_views, len(mine)), dtype=torch.float32, device=device)
             chunk = min(int(getattr(renderer, "max_candidates_per_launch", vision.max_batch)), vision.max_batch)
-            for v, s, e, frames, rects, bg_u8 in renderer.iter_render(valid_poses_ngp[lo:hi], render_poses_ngp, render_cam_pose_idx, depths_gt,
+            for v, s, e, frames, rects, bg_u8 in renderer.iter_render(valid_poses_ngp[mine], render_poses_ngp, render_cam_pose_idx, depths_gt,
                                                                       task_model.movable_masks, save=save_renders and world == 1, chunk=chunk):
                 emb = vision.encode_images(frames, rot90=True, bg_u8=bg_u8, rects=rects)
                 local[v, s:e] = vision.score(emb, txt, n_goal=n_goal)
@@ -192,7 +210,7 @@ def optimise_pose_grid(renderer,
             local = score_renders(renders, vision, txt, n_goal=n_goal)
         else:
             local = torch.zeros(0, dtype=torch.float32, device=device)
-        logits = gather_scores(local, valid_idxs.shape[0], world, rank) if world > 1 else local
+        logits = gather_scores(local, valid_idxs.shape[0], world, rank, mode=shard) if world > 1 else local
         logits = logits.to('cpu')
 
     pose_scores = torch.zeros(pose_batch.shape[0])

@@ -432,7 +432,7 @@ using namespace d2r;
 
 extern "C" void d2r_clip_free(d2r_clip* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard dg(c->device);
     for (void* p : c->allocs) cudaFree(p);
     delete c;
 }
@@ -448,7 +448,7 @@ extern "C" int d2r_clip_load(const d2r_clip_cfg* cfg, const float* const* W, int
     D2R_REQUIRE(cfg->max_batch > 0, "d2r_clip_load: max_batch must be positive");
     D2R_REQUIRE(n_weights == 5 + 16 * L + 3, "d2r_clip_load: expected 5 + 16*layers + 3 weight tensors");
     for (int i = 0; i < n_weights; ++i) D2R_REQUIRE(W[i] != nullptr, "d2r_clip_load: null weight pointer");
-    D2R_CUDA(cudaSetDevice(device));
+    DeviceGuard dg(device);
     d2r_clip* c = new d2r_clip();
     c->device = device;
     c->cfg = *cfg;
@@ -539,7 +539,7 @@ extern "C" int d2r_clip_encode(d2r_clip* c, const void* patches_dev, int B, floa
     cudaStream_t stream = (cudaStream_t)stream_;
     D2R_REQUIRE(c && patches_dev && embeds_out_dev, "d2r_clip_encode: null argument");
     D2R_REQUIRE(B > 0 && B <= c->cfg.max_batch, "d2r_clip_encode: batch exceeds max_batch");
-    D2R_CUDA(cudaSetDevice(c->device));
+    DeviceGuard dg(c->device);
     const int d = c->cfg.hidden, T = c->T, mlp = c->cfg.mlp, M = B * T;
     const float eps = c->cfg.ln_eps;
     int rc;

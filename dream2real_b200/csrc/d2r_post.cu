@@ -10,6 +10,8 @@
 // reference (requirements.txt: Pillow==9.4.0), not vendored under /root/reference.
 #include <math.h>
 
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "d2r_common.cuh"
@@ -306,14 +308,24 @@ struct ResizePlan {
     int* bounds_dev = nullptr;
     int* kk_dev = nullptr;
 };
+// resize coefficient tables: read-only once built, shared per device (guarded); scratch: per (device, stream), so two host threads
+// driving two streams of one GPU never share it (kernels of one stream run in order, so one set per stream is enough)
+static std::mutex g_post_mutex;
 static std::vector<ResizePlan> g_plans[16];
-static uint8_t* g_tmp[16] = {nullptr};
-static size_t g_tmp_cap[16] = {0};
 struct DeltaScratch { uint8_t* bg_tmp = nullptr; size_t bg_tmp_cap = 0; __half* bg_patches = nullptr; size_t bg_patches_cap = 0;
                       DeltaRange* ranges = nullptr; int ranges_cap = 0; };
-static DeltaScratch g_delta[16];
+struct PostCtx { uint8_t* tmp = nullptr; size_t tmp_cap = 0; DeltaScratch delta; };
+static std::map<std::pair<int, cudaStream_t>, PostCtx*> g_post_ctx;
+
+static PostCtx* get_post_ctx(int device, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(g_post_mutex);
+    PostCtx*& c = g_post_ctx[std::make_pair(device, stream)];
+    if (!c) c = new PostCtx();
+    return c;
+}
 
 static int get_plan(int device, int in_size, int out_size, ResizePlan* out) {
+    std::lock_guard<std::mutex> lock(g_post_mutex);
     for (const ResizePlan& p : g_plans[device])
         if (p.in_size == in_size && p.out_size == out_size) { *out = p; return D2R_OK; }
     ResizePlan p;
@@ -354,12 +366,14 @@ extern "C" int d2r_clip_preprocess(const uint8_t* rgb_u8_dev, int K, int H, int 
     if (rc) return rc;
     const ResizePlan *ph = &ph_, *pv = &pv_;
     const size_t tmp_bytes = (size_t)K * R * Hr * 3 + 16;   // + slack: the vertical pass reads whole aligned words
-    if (tmp_bytes > g_tmp_cap[device]) {
-        if (g_tmp[device]) D2R_CUDA(cudaFree(g_tmp[device]));
-        D2R_CUDA(cudaMalloc(&g_tmp[device], tmp_bytes));
-        g_tmp_cap[device] = tmp_bytes;
+    PostCtx& ctx = *get_post_ctx(device, stream);
+    if (tmp_bytes > ctx.tmp_cap) {
+        if (ctx.tmp) D2R_CUDA(cudaFree(ctx.tmp));
+        ctx.tmp = nullptr; ctx.tmp_cap = 0;
+        D2R_CUDA(cudaMalloc(&ctx.tmp, tmp_bytes));
+        ctx.tmp_cap = tmp_bytes;
     }
-    rc = run_full_resize(rgb_u8_dev, K, H, W, rot90, R, P, mean, std_, ph, pv, g_tmp[device], (__half*)patches_out_dev, pixels_f32_out_dev, stream);
+    rc = run_full_resize(rgb_u8_dev, K, H, W, rot90, R, P, mean, std_, ph, pv, ctx.tmp, (__half*)patches_out_dev, pixels_f32_out_dev, stream);
     if (rc) return rc;
     D2R_CUDA(cudaGetLastError());
     return D2R_OK;
@@ -407,12 +421,14 @@ extern "C" int d2r_clip_preprocess_delta(const uint8_t* rgb_u8_dev, int K, int H
     rc = get_plan(device, Hr, R, &pv);
     if (rc) return rc;
     const size_t tmp_bytes = (size_t)K * R * Hr * 3 + 16;
-    if (tmp_bytes > g_tmp_cap[device]) {
-        if (g_tmp[device]) D2R_CUDA(cudaFree(g_tmp[device]));
-        D2R_CUDA(cudaMalloc(&g_tmp[device], tmp_bytes));
-        g_tmp_cap[device] = tmp_bytes;
+    PostCtx& ctx = *get_post_ctx(device, stream);
+    if (tmp_bytes > ctx.tmp_cap) {
+        if (ctx.tmp) D2R_CUDA(cudaFree(ctx.tmp));
+        ctx.tmp = nullptr; ctx.tmp_cap = 0;
+        D2R_CUDA(cudaMalloc(&ctx.tmp, tmp_bytes));
+        ctx.tmp_cap = tmp_bytes;
     }
-    DeltaScratch& ds = g_delta[device];
+    DeltaScratch& ds = ctx.delta;
     const int K0 = 3 * P * P, Kp = (K0 + 63) / 64 * 64, np = (R / P) * (R / P);
     const size_t bg_tmp_bytes = (size_t)R * Hr * 3 + 16, bg_patch_elems = (size_t)np * Kp;
     if (bg_tmp_bytes > ds.bg_tmp_cap) {
@@ -438,8 +454,8 @@ extern "C" int d2r_clip_preprocess_delta(const uint8_t* rgb_u8_dev, int K, int H
     const size_t n16 = bg_patch_elems * sizeof(__half) / 16;       // Kp is a multiple of 64 halves
     k_copy_patches<<<dim3(8, K), 256, 0, stream>>>((const uint4*)ds.bg_patches, n16, (uint4*)patches_out_dev);
     k_resize_h_delta<<<dim3(2, 64, K), 128, 0, stream>>>(rgb_u8_dev, H, W, rot90, Hr, R, ph.ksize, ph.bounds_dev, ph.kk_dev, ds.ranges,
-                                                         g_tmp[device]);
-    k_resize_v_delta<<<dim3(1, 64, K), 64, 0, stream>>>(g_tmp[device], ds.bg_tmp, Hr, R, pv.ksize, pv.bounds_dev, pv.kk_dev, ds.ranges, P, Kp,
+                                                         ctx.tmp);
+    k_resize_v_delta<<<dim3(1, 64, K), 64, 0, stream>>>(ctx.tmp, ds.bg_tmp, Hr, R, pv.ksize, pv.bounds_dev, pv.kk_dev, ds.ranges, P, Kp,
                                                         mean[0], mean[1], mean[2], std_[0], std_[1], std_[2], (__half*)patches_out_dev);
     count_launch(4);
     D2R_CUDA(cudaGetLastError());

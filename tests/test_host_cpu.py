@@ -168,12 +168,15 @@ def test_shard_bounds():
 
 def _gloo_worker(rank, world, port, n, q):
     import torch.distributed as dist
-    from dream2real_b200.clip_scoring import gather_scores, shard_bounds
+    from dream2real_b200.clip_scoring import gather_scores, shard_bounds, shard_indices
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     full = torch.arange(n, dtype=torch.float32) * 0.5 + 1
     lo, hi = shard_bounds(n, world, rank)
-    out = gather_scores(full[lo:hi].clone(), n, world, rank)
-    q.put((rank, torch.equal(out, full)))
+    ok = torch.equal(gather_scores(full[lo:hi].clone(), n, world, rank), full)
+    for mode in ("contiguous", "strided"):      # both splits come back in the candidates' original order
+        idx = shard_indices(n, world, rank, mode)
+        ok = ok and torch.equal(gather_scores(full[idx].clone(), n, world, rank, mode=mode), full)
+    q.put((rank, ok))
     dist.destroy_process_group()
 
 
