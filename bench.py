@@ -263,8 +263,16 @@ def measure(args, world_ctx, scene_name, K, grid, sharded, steps, warmup, sample
     if world > 1:
         dist.all_reduce(tot)
     total = int(tot.item())
+    # every rank's own time for the same timed region (each step ends with the all-gather, so these are near-equal; the
+    # per-rank march time shows which GPU set the pace)
+    mine = torch.tensor([float(mm.value) / max(1, steps)], device=device)
+    per_rank = [mine.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine)
+    march_ms_ranks = [round(float(t.item()), 2) for t in per_rank]
     return dict(scene=scene, scene_dir=scene_dir, K=K, total=total, grid=grid_res, ms=ms, ms_e2e=ms_e2e, vit_ms=vit_ms, clocks=clk,
-                launches=int(launches), march_ms=float(mm.value), march_launches=int(nl.value), samples=int(ns.value), rays=int(nt.value))
+                launches=int(launches), march_ms=float(mm.value), march_launches=int(nl.value), samples=int(ns.value), rays=int(nt.value),
+                march_ms_ranks=march_ms_ranks)
 
 
 def run_ours(args):
@@ -343,6 +351,7 @@ def run_ours(args):
                      "traffic_note": traffic_note, "algorithmic_bytes_per_launch": alg_bytes / max(1, m["march_launches"]), "peak_source": peak_src,
                      "launches": m["march_launches"], "launches_per_step": launches_per_step,
                      "avg_launch_ms": m["march_ms"] / max(1, m["march_launches"]), "share_of_step": m["march_ms"] / m["ms"],
+                     "march_ms_per_step_by_rank": m["march_ms_ranks"],
                      "note": "algorithmic bytes (512 B of table reads per sample + 23 B per primary ray); the hash tables (~25 MB) are L2-resident, so "
                              "the table reads are L2 traffic, not DRAM traffic (SURVEY.md 8(d) caveat): `traffic` (DRAM) and `l2_traffic` (lts) are the "
                              "measured bytes per launch next to the algorithmic figure"},

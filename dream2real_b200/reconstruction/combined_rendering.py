@@ -103,7 +103,7 @@ class renderer:
             os.makedirs(self.out_render_path)
         self.last_n_samples = 0
         fg = self.fg_obj.vis_model
-        inv_T_WO_2 = np.linalg.inv(valid_poses)                                   # [K,4,4]
+        inv_T_WO_2 = None                                                          # [K,4,4], computed while the GPU renders the background
         dev = torch.device("cuda", fg.device)
         buf = None if out is not None else torch.empty((min(chunk, K), H, W, 3), dtype=torch.uint8, device=dev)
         rect_buf = torch.empty((min(chunk, K), 4), dtype=torch.int32, device=dev) if out is None else None
@@ -116,6 +116,8 @@ class renderer:
                 None if depths_gt is None else movable_masks[mask_idx])
             fg.set_camera_to_training_view(view_idx)
             fg.render_ground_truth = False
+            if inv_T_WO_2 is None:
+                inv_T_WO_2 = np.linalg.inv(valid_poses)
             # T_WC_2 = T_WO_1 . (T_WO_2^-1 . T_WO_1) . (T_WO_1^-1 . T_WC_1), same association as the reference
             cams = T_WO_1 @ (inv_T_WO_2 @ T_WO_1) @ (np.linalg.inv(T_WO_1) @ T_WC_1)
             bg_u8 = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
