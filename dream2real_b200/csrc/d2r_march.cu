@@ -353,7 +353,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
         D2R_CUDA(cudaMemsetAsync(s.sp_cnt, 0, (256 + 2) * sizeof(uint32_t), stream));
         static bool split_attr[16] = {false};
         if (!split_attr[m->device]) {
-            D2R_CUDA(cudaFuncSetAttribute(k_mlp_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_TOTAL));
+            D2R_CUDA(cudaFuncSetAttribute(k_mlp_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_TOTAL));
             split_attr[m->device] = true;
         }
         SplitParams Q;
@@ -366,7 +366,7 @@ int launch_march(const d2r_model* m, const d2r_view* v, const float* cams_ngp_ho
             Q.live_in = s.sp_live[r & 1]; Q.live_out = s.sp_live[(r + 1) & 1];
             Q.acc4_in = s.sp_acc4[r & 1]; Q.acca_in = s.sp_acca[r & 1]; Q.acc4_out = s.sp_acc4[(r + 1) & 1]; Q.acca_out = s.sp_acca[(r + 1) & 1];
             k_gather_round<<<s.n_sm * 7, 128, 0, stream>>>(P, Q);
-            k_mlp_round<<<s.n_sm * 3, TC_THREADS, T2_TOTAL, stream>>>(P, Q);
+            k_mlp_round<<<s.n_sm, 128 * TS_GROUPS, TS_TOTAL, stream>>>(P, Q);
             count_launch(2);
         }
         // the survivors: a live ray of round r has taken exactly 2 r samples

@@ -1,13 +1,11 @@
-// Round-based split of the ray march (D2R_MARCH=split; kept as the A/B partner of k_march_ws): k_gather_round (walk + hash-grid gather, no barriers, no tensor-core state ->
-// few registers, many warps per SM) and k_mlp_round (the five MLP layers on tcgen05 + compositing), alternating until no
-// ray is left.  Included by d2r_march.cu after d2r_march_common.cuh.
+// Round-based split of the ray march: k_gather_round (walk + hash-grid gather, no barriers, no tensor-core state -> few
+// registers, many warps per SM) and k_mlp_round (the five MLP layers on tcgen05 + compositing), alternating for a fixed number
+// of rounds; whatever is still alive then resumes in k_march_ws.  Included by d2r_march.cu after d2r_march_common.cuh.
 //
-// Why (round 1): a fused kernel whose threads do everything runs at 16 warps per SM -- 128 registers per thread, all TMEM columns, 208 KB of
-// shared memory -- and every component's latency (walk, gather, five MMA round trips) is exposed in full: the kernel's time
-// does not depend on the table size (2^14 vs 2^19 entries: same time per sample), doubling the gather adds 55 %, doubling
-// the walk 17 % (profiles/).  The gather needs neither TMEM nor shared memory, so on its own it runs at 3x the occupancy.
-// Price: 64 B of fp16 features per sample go through HBM once (written in the UMMA canonical operand layout, so the MLP
-// kernel stages them with plain 16-byte copies), plus 24 B of per-ray accumulators per round.
+// Why: a fused kernel whose threads do everything runs at 16 gather warps per SM next to its tensor-core state, and every
+// component's latency (walk, gather, five MMA round trips) is exposed; the gather needs neither TMEM nor shared memory, so on
+// its own it runs at 28 warps per SM.  Price: 64 B of fp16 features per sample go through HBM once (written in the UMMA
+// canonical operand layout, so k_mlp_round stages a block's two tiles with one bulk copy), plus the per-ray accumulators.
 //
 // Per round r every live ray takes its next (up to) two samples -- the same walk, features and compositing arithmetic as
 // k_march_ws, so the results are identical; a ray that finishes keeps its accumulators in res_rgbd / res_a (k_finish turns
@@ -132,52 +130,94 @@ __global__ void __launch_bounds__(128, 7) k_gather_round(const __grid_constant__
     (void)my_samples;
 }
 
-// shared memory plan of k_mlp_round (bytes): weights, 2 tiles whose K=32 and K=64 operands alias, and the feature staging
-// buffer the bulk copies land in (68 KB -> 3 CTAs per SM)
-constexpr int T2_A64 = W_BYTES;
-constexpr int T2_A32 = T2_A64;
-constexpr int T2_TILE = 16384;
-constexpr int T2_FEAT = T2_A64 + 2 * T2_TILE;          // [2][8 KB]: a block's two sample tiles exactly as k_gather_round wrote them
-constexpr int T2_MISC = T2_FEAT + 2 * SPLIT_TILE_BYTES;
-constexpr int T2_TOTAL = T2_MISC + 256;
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_mlp_round: the five MLP layers of a round's samples on tcgen05, the activations kept in TENSOR MEMORY between layers
+// ("TS" operand mode), then the compositing and the live-list append.
+//
+// tools/tmem_port_bench.cu (profiles/r2_tmem_port_bench.json): one layer of one 128-sample tile is a ~1000-cycle dependent
+// chain (MMA round trip ~780 cycles), SS-mode MMAs spend most of their time fetching the 128-row A operand from shared memory,
+// and throughput = tiles in flight / chain length.  Here a thread's ReLU'd fp16 row goes back with tcgen05.st into 32 columns
+// next to the accumulators and the next layer's MMAs read A from there: no shared-memory operand rows, no proxy fences, MMAs of
+// 32 / 8 cycles instead of 48 / 39.  A tile needs 96 columns, so an SM holds five: five independent 128-thread groups per CTA,
+// each taking its block's two sample tiles through the layers one after the other (the other four groups fill its round
+// trips); the MMAs of a layer leave back to back from an elected lane of the group's converged first warp with warp-uniform
+// descriptors.  Only the first layer is SS: its A operand is the block's feature tiles (16 KB, contiguous, already in UMMA
+// operand layout), which ONE cp.async.bulk lands in the group's staging buffer -- no thread touches them -- issued for the
+// next block as soon as this block's first layers have retired.  A block's live-list append is finished during the next
+// block's first MMA wait (the atomic's round trip is off the critical path).
+// Same arithmetic per sample as k_march_ws (same MMA shapes and K order, same rounding points): identical frames.
+// The shared-memory-operand form this replaces (3 CTAs x 2 skewed tiles per SM) took 43 ms of a 191 ms step, this one 30.
+constexpr int TS_GROUPS = 5;
+constexpr int TS_COLS = 96;                                   // per group: accumulators [0, 64) + fp16 operand rows [64, 96)
+constexpr int TS_FEAT_BYTES = 2 * SPLIT_TILE_BYTES;           // per group: a block's two staged sample tiles
+constexpr int TS_MISC = W_BYTES + TS_GROUPS * TS_FEAT_BYTES;
+constexpr int TS_TOTAL = TS_MISC + 32 * TS_GROUPS + 64;
 
-// A block's two feature tiles (16 KB, contiguous, already in UMMA operand layout) arrive with ONE cp.async.bulk straight into the
-// buffer the first layer's MMAs read: no thread touches them.  The copy for the next block is issued as soon as those MMAs
-// have retired, so it flies during the other four layers; a block's live-list append is finished during the next block's
-// first MMA wait (the atomic's round trip is off the critical path).
-__global__ void __launch_bounds__(TC_THREADS, 3) k_mlp_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_ts_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 db;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(b_lo), "r"(hi), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+}
+// D[128 x N] = A[128 x K] (TMEM: row = lane, two fp16 per 32-bit column) * W[N x K]^T (shared memory, K-major, no swizzle)
+template <int K, int N>
+__device__ __forceinline__ void issue_tile_ts(uint32_t tmem_a, uint32_t b_lo, uint32_t tmem_d) {
+    constexpr uint32_t hi = (uint32_t)((K / 8) * 128 >> 4) | (1u << 14);
+    constexpr uint32_t idesc = umma_idesc_f16(128, N, 0);
+    umma_f16_ts_lohi<false>(tmem_d, tmem_a, b_lo, hi, idesc);
+#pragma unroll
+    for (int kk = 1; kk < K / 16; ++kk) umma_f16_ts_lohi<true>(tmem_d, tmem_a + kk * 8, b_lo + kk * 16, hi, idesc);
+}
+__device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(128 * TS_GROUPS, 1) k_mlp_round(const __grid_constant__ MarchParams P, const __grid_constant__ SplitParams Q) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (*P.n_entries > Q.cap) return;
     const ModelDev& M = P.M;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + T2_MISC);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T2_MISC + 16);      // (mbarriers at +0, +8, +24)
+    // the warp index as a value the compiler knows to be warp-uniform: descriptors, TMEM and mbarrier addresses of the issue
+    // path then live in uniform registers (no per-lane R2UR waterfall in front of every tcgen05.mma)
+    const int warp_cta = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int grp = warp_cta >> 2, warp = warp_cta & 3, tid = threadIdx.x & 127, lane = tid & 31;      // warp, tid: within the group
+    unsigned char* feat = smem + W_BYTES + grp * TS_FEAT_BYTES;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + TS_MISC + 32 * grp);      // [0] the group's MMAs, [1] its staged features
+    uint64_t* bar_feat = mbar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TS_MISC + 32 * TS_GROUPS);
+    const uint32_t vblk0 = blockIdx.x * TS_GROUPS + grp, vstride = gridDim.x * TS_GROUPS;
+    auto group_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); };
 
-    for (int i = tid; i < W_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(M.w_umma)[i];
-    uint64_t* bar_feat = mbar + 3;
-    if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); mbar_init(bar_feat, 1); fence_barrier_init(); }
-    if (warp == 0) tmem_alloc<128>(tmem_slot);
+    for (int i = threadIdx.x; i < W_BYTES / 16; i += 128 * TS_GROUPS) reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(M.w_umma)[i];
+    if (tid == 0) { mbar_init(mbar, 1); mbar_init(bar_feat, 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) tmem_alloc<512>(tmem_slot);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const uint32_t a64 = smem_u32(smem + T2_A64);
-    unsigned char* rowA32 = smem + T2_A32 + umma_chunk_off(tid, 0, 32);
-    unsigned char* rowA64 = smem + T2_A64 + umma_chunk_off(tid, 0, 64);
-    uint32_t phase0 = 0, phase1 = 0, phase_feat = 0;
+    const uint32_t tmem_all = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const uint32_t tmem_d = tmem_all + TS_COLS * grp, tmem_a = tmem_d + 64;
+    const uint32_t lane_d = tmem_d + ((uint32_t)(warp * 32) << 16), lane_a = lane_d + 64;
     const uint32_t n_live = Q.round == 0 ? *P.n_entries : *Q.cnt_in;
-    const uint32_t f_lo = (smem_u32(smem + T2_FEAT) >> 4) + (8u << 16);
-    auto fetch_features = [&](uint32_t b) {      // tid 0: the two sample tiles of block b -> staging buffer
-        mbar_arrive_expect_tx(bar_feat, 2 * SPLIT_TILE_BYTES);
-        bulk_g2s(smem + T2_FEAT, Q.feat + (size_t)b * 2 * SPLIT_TILE_BYTES, 2 * SPLIT_TILE_BYTES, bar_feat);
+    const uint32_t f_lo = (smem_u32(feat) >> 4) + (8u << 16), w_lo = (smem_u32(smem) >> 4) + (8u << 16);
+    uint32_t phase = 0, phase_feat = 0;
+    auto fetch_features = [&](uint32_t b) {      // tid 0: the two sample tiles of block b -> the group's staging buffer
+        mbar_arrive_expect_tx(bar_feat, TS_FEAT_BYTES);
+        bulk_g2s(feat, Q.feat + (size_t)b * TS_FEAT_BYTES, TS_FEAT_BYTES, bar_feat);
     };
-    if (tid == 0 && (size_t)blockIdx.x * 128 < n_live) fetch_features(blockIdx.x);
+    if (tid == 0 && (size_t)vblk0 * 128 < n_live) fetch_features(vblk0);
     unsigned long long my_samples = 0, my_rays = 0;
-    // descriptor low words ((address >> 4) | LBO 128 B): the issuing thread's path is a handful of 32-bit adds per MMA
-    const uint32_t a_lo = (a64 >> 4) + (8u << 16), w_lo = (smem_u32(smem) >> 4) + (8u << 16);
-    // the previous block's live-list append (its atomic is already in flight): entry id and accumulators of the rays that go on
     uint32_t pend_go = 0, pend_base = 0, pend_e = 0;
     bool pend_alive = false;
     float4 pend_a4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -194,128 +234,96 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_mlp_round(const __grid_consta
             pend_go = 0;
         }
     };
-    // Everything a block reads per ray is indexed by the ray's POSITION in this round's list (coalesced), and is fetched one
-    // block ahead: the loads are issued after the last proxy fence of the previous block, so no fence ever waits for them.
-    struct In { uint32_t ns_raw, e; uint4 sh0, sh1; float2 ax0, ax1; float4 a4; float aa; };
-    auto load_inputs = [&](uint32_t b) {
-        In in;
-        const uint32_t i = b * 128 + tid;
-        in.ns_raw = 0u; in.e = 0u; in.sh0 = in.sh1 = make_uint4(0, 0, 0, 0); in.ax0 = in.ax1 = make_float2(0.f, 0.f);
-        in.a4 = make_float4(0.f, 0.f, 0.f, 0.f); in.aa = 0.f;
-        if (i < n_live) {
-            in.ns_raw = Q.nsb[i] | 0x100u;                                   // bit 8: a ray sits at this position
-            in.e = Q.round == 0 ? i : Q.live_in[i];
-            in.sh0 = Q.shb[(size_t)i * 2]; in.sh1 = Q.shb[(size_t)i * 2 + 1];
-            in.ax0 = Q.aux[((size_t)b * 2 + 0) * 128 + tid];
-            in.ax1 = Q.aux[((size_t)b * 2 + 1) * 128 + tid];
-            if (Q.round > 0) { in.a4 = Q.acc4_in[i]; in.aa = Q.acca_in[i]; }
-        }
-        return in;
-    };
-    In nxt = load_inputs(blockIdx.x);
-    for (uint32_t blk = blockIdx.x; (size_t)blk * 128 < n_live; blk += gridDim.x) {
-        const In cur = nxt;
-        const bool valid = (cur.ns_raw & 0x100u) != 0;
-        const int n_s = (int)(cur.ns_raw & 15u);
-        const bool exits = (cur.ns_raw & 16u) != 0;
-        const uint32_t e = cur.e;
-        float cr = cur.a4.x, cg = cur.a4.y, cb = cur.a4.z, cd = cur.a4.w, ca = cur.aa;
-        const uint4 sh0 = cur.sh0, sh1 = cur.sh1;
-        const float2 ax0 = cur.ax0, ax1 = cur.ax1;
-        if (valid && Q.round == 0) ++my_rays;
-        // The five layers, the two sample tiles skewed against each other: each tile has its own mbarrier and its own TMEM
-        // columns, and the MMAs of one tile's next layer are issued the moment its rows are written -- they run while every
-        // thread is busy with the other tile's tcgen05.ld / ReLU / fp16 pack / store.  (Issuing is a handful of 32-bit adds
-        // per MMA: issue_tile_ws.)
-        auto wait_tile = [&](int s) {
-            if (s == 0) { mbar_wait(mbar, phase0); phase0 ^= 1; } else { mbar_wait(mbar + 1, phase1); phase1 ^= 1; }
-            tc_fence_after();
-        };
-        auto hidden_rows = [&](int s) {      // 64 outputs, ReLU, fp16 -> the tile's K=64 operand rows
-            uint32_t r[64];
-            tmem_ld_32x32_x64(tmem_lane + s * 64, r);
-            tmem_ld_wait();
+    auto wait_mma = [&]() { mbar_wait(mbar, phase); phase ^= 1; tc_fence_after(); };
+    auto rows_done = [&]() { tmem_st_wait(); tc_fence_before(); group_barrier(); };
+    auto hidden_rows = [&]() {      // 64 outputs, ReLU, fp16 -> this thread's row of the next layer's A operand (32 columns)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint4 v;
-                v.x = pack_relu_h2(r[8 * c + 0], r[8 * c + 1], true); v.y = pack_relu_h2(r[8 * c + 2], r[8 * c + 3], true);
-                v.z = pack_relu_h2(r[8 * c + 4], r[8 * c + 5], true); v.w = pack_relu_h2(r[8 * c + 6], r[8 * c + 7], true);
-                *reinterpret_cast<uint4*>(rowA64 + s * T2_TILE + c * 128) = v;
-            }
-        };
-        auto rows_done = [&]() { fence_proxy_async(); tc_fence_before(); __syncthreads(); };
-        // ---- density layer 0: 32 -> 64, ReLU; A = the staged feature tiles ----
-        if (tid == 0) {
-            mbar_wait(bar_feat, phase_feat);
-            tc_fence_after();
-            issue_tile_ws<32, 64>(f_lo, w_lo + (W_D0 >> 4), tmem_base); tc_commit(mbar);
-            issue_tile_ws<32, 64>(f_lo + (SPLIT_TILE_BYTES >> 4), w_lo + (W_D0 >> 4), tmem_base + 64); tc_commit(mbar + 1);
+        for (int h = 0; h < 2; ++h) {      // in halves, 32 accumulators -> 16 packed columns: five groups share the register file
+            uint32_t r[32];                //   (both loads in flight at once spills and measured 4 % slower per step)
+            tmem_ld_32x32(lane_d + 32 * h, r);
+            tmem_ld_wait();
+            uint32_t v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = pack_relu_h2(r[2 * j], r[2 * j + 1], true);
+            tmem_st_32x32_x16(lane_a + 16 * h, v);
         }
-        phase_feat ^= 1;
-        flush_append();          // the previous block's append: its atomic returned long ago
+    };
+    for (uint32_t blk = vblk0; (size_t)blk * 128 < n_live; blk += vstride) {
+        // Everything a block reads per ray is indexed by the ray's POSITION in this round's list (coalesced); the loads leave
+        // now and are first needed a layer (SH), or all ten layers (the rest), later.
+        const uint32_t i = blk * 128 + tid;
+        const bool valid = i < n_live;
+        uint32_t ns_raw = 0, e = 0;
+        uint4 sh0 = make_uint4(0, 0, 0, 0), sh1 = sh0;
+        float2 ax0 = make_float2(0.f, 0.f), ax1 = ax0;
+        float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, ca = 0.f;
+        if (valid) {
+            ns_raw = Q.nsb[i];
+            e = Q.round == 0 ? i : Q.live_in[i];
+            sh0 = Q.shb[(size_t)i * 2]; sh1 = Q.shb[(size_t)i * 2 + 1];
+            ax0 = Q.aux[((size_t)blk * 2 + 0) * 128 + tid];
+            ax1 = Q.aux[((size_t)blk * 2 + 1) * 128 + tid];
+            if (Q.round > 0) { const float4 a4 = Q.acc4_in[i]; cr = a4.x; cg = a4.y; cb = a4.z; cd = a4.w; ca = Q.acca_in[i]; }
+            if (Q.round == 0) ++my_rays;
+        }
+        float sigma[2], raw[2][3];
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            wait_tile(s);
-            if (s == 1 && tid == 0) {      // both tiles' first-layer MMAs have retired: the staging buffer is free for the next block
-                const uint32_t nb = blk + gridDim.x;
+            // ---- density layer 0: 32 -> 64, ReLU; A = the staged feature tile (shared memory) ----
+            if (warp == 0) {
+                if (s == 0) mbar_wait(bar_feat, phase_feat);
+                tc_fence_after();
+                if (elect_one()) { issue_tile_ws<32, 64>(f_lo + s * (SPLIT_TILE_BYTES >> 4), w_lo + (W_D0 >> 4), tmem_d); tc_commit(mbar); }
+                __syncwarp();
+            }
+            if (s == 0) flush_append();          // the previous block's append: its atomic returned long ago
+            wait_mma();
+            if (s == 1 && tid == 0) {            // both tiles' first layers have retired: the staging buffer is free for the next block
+                const uint32_t nb = blk + vstride;
                 if ((size_t)nb * 128 < n_live) fetch_features(nb);
             }
-            hidden_rows(s);
+            hidden_rows();
             rows_done();
             // ---- density layer 1: 64 -> 16 (row 0 = raw density) ----
-            if (tid == 0) { tc_fence_after(); issue_tile_ws<64, 16>(a_lo + s * 1024, w_lo + (W_D1 >> 4), tmem_base + s * 64); tc_commit(mbar + s); }
-        }
-        float sigma0 = 0.f, sigma1 = 0.f;
+            if (warp == 0) { tc_fence_after(); if (elect_one()) { issue_tile_ts<64, 16>(tmem_a, w_lo + (W_D1 >> 4), tmem_d); tc_commit(mbar); } __syncwarp(); }
+            wait_mma();
+            {
+                uint32_t r[16];
+                tmem_ld_32x32_x16(lane_d, r);
+                tmem_ld_wait();
+                sigma[s] = h2f_round(__uint_as_float(r[0]));
+                uint32_t v[16];      // rgb input = [16 density-out | 16 SH]
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            wait_tile(s);
-            uint32_t r[16];
-            tmem_ld_32x32_x16(tmem_lane + s * 64, r);
-            tmem_ld_wait();
-            const float sg = h2f_round(__uint_as_float(r[0]));
-            if (s == 0) sigma0 = sg; else sigma1 = sg;
-            uint4 v0, v1;
-            v0.x = pack_relu_h2(r[0], r[1], false); v0.y = pack_relu_h2(r[2], r[3], false);
-            v0.z = pack_relu_h2(r[4], r[5], false); v0.w = pack_relu_h2(r[6], r[7], false);
-            v1.x = pack_relu_h2(r[8], r[9], false); v1.y = pack_relu_h2(r[10], r[11], false);
-            v1.z = pack_relu_h2(r[12], r[13], false); v1.w = pack_relu_h2(r[14], r[15], false);
-            unsigned char* row = rowA32 + s * T2_TILE;      // rgb input = [16 density-out | 16 SH]
-            *reinterpret_cast<uint4*>(row + 0) = v0;
-            *reinterpret_cast<uint4*>(row + 128) = v1;
-            *reinterpret_cast<uint4*>(row + 256) = sh0;
-            *reinterpret_cast<uint4*>(row + 384) = sh1;
+                for (int j = 0; j < 8; ++j) v[j] = pack_relu_h2(r[2 * j], r[2 * j + 1], false);
+                v[8] = sh0.x; v[9] = sh0.y; v[10] = sh0.z; v[11] = sh0.w; v[12] = sh1.x; v[13] = sh1.y; v[14] = sh1.z; v[15] = sh1.w;
+                tmem_st_32x32_x16(lane_a, v);
+            }
             rows_done();
             // ---- rgb layer 0: 32 -> 64, ReLU ----
-            if (tid == 0) { tc_fence_after(); issue_tile_ws<32, 64>(a_lo + s * 1024, w_lo + (W_C0 >> 4), tmem_base + s * 64); tc_commit(mbar + s); }
-        }
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            wait_tile(s);
-            hidden_rows(s);
+            if (warp == 0) { tc_fence_after(); if (elect_one()) { issue_tile_ts<32, 64>(tmem_a, w_lo + (W_C0 >> 4), tmem_d); tc_commit(mbar); } __syncwarp(); }
+            wait_mma();
+            hidden_rows();
             rows_done();
             // ---- rgb layer 1: 64 -> 64, ReLU ----
-            if (tid == 0) { tc_fence_after(); issue_tile_ws<64, 64>(a_lo + s * 1024, w_lo + (W_C1 >> 4), tmem_base + s * 64); tc_commit(mbar + s); }
-        }
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            wait_tile(s);
-            hidden_rows(s);      // in place: the MMA that read these rows has retired
+            if (warp == 0) { tc_fence_after(); if (elect_one()) { issue_tile_ts<64, 64>(tmem_a, w_lo + (W_C1 >> 4), tmem_d); tc_commit(mbar); } __syncwarp(); }
+            wait_mma();
+            hidden_rows();
             rows_done();
             // ---- rgb output layer: 64 -> 16 (3 used) ----
-            if (tid == 0) { tc_fence_after(); issue_tile_ws<64, 16>(a_lo + s * 1024, w_lo + (W_C2 >> 4), tmem_base + s * 64); tc_commit(mbar + s); }
+            if (warp == 0) { tc_fence_after(); if (elect_one()) { issue_tile_ts<64, 16>(tmem_a, w_lo + (W_C2 >> 4), tmem_d); tc_commit(mbar); } __syncwarp(); }
+            wait_mma();
+            {
+                uint32_t r[16];
+                tmem_ld_32x32_x16(lane_d, r);
+                tmem_ld_wait();
+                raw[s][0] = h2f_round(__uint_as_float(r[0])); raw[s][1] = h2f_round(__uint_as_float(r[1])); raw[s][2] = h2f_round(__uint_as_float(r[2]));
+            }
+            tc_fence_before();
+            group_barrier();      // every thread has read its output row: the next tile's first MMAs may overwrite the accumulators
         }
-        // that was this block's last proxy fence: the next block's per-ray inputs start their way now and land during the
-        // output layer, the compositing and the next block's first layer
-        nxt = load_inputs(blk + gridDim.x);
-        float raw[2][3];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            wait_tile(s);
-            uint32_t r[16];
-            tmem_ld_32x32_x16(tmem_lane + s * 64, r);
-            tmem_ld_wait();
-            raw[s][0] = h2f_round(__uint_as_float(r[0])); raw[s][1] = h2f_round(__uint_as_float(r[1])); raw[s][2] = h2f_round(__uint_as_float(r[2]));
-        }
+        phase_feat ^= 1;
+        const int n_s = (int)(ns_raw & 15u);
+        const bool exits = (ns_raw & 16u) != 0;
         // ---- composite_kernel_nerf (testbed_nerf.cu:511-667), sample 0 then sample 1; same arithmetic as k_march_ws ----
         bool alive = valid;
         if (alive) {
@@ -324,7 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_mlp_round(const __grid_consta
                 if (alive && s < n_s) {
                     ++my_samples;
                     const float T = 1.f - ca;
-                    const float alpha = 1.f - __expf(-__expf(s == 0 ? sigma0 : sigma1) * (s == 0 ? ax0.y : ax1.y));
+                    const float alpha = 1.f - __expf(-__expf(sigma[s]) * (s == 0 ? ax0.y : ax1.y));
                     const float weight = alpha * T;
                     const float rr = logistic_d(raw[s][0]), gg = logistic_d(raw[s][1]), bb_ = logistic_d(raw[s][2]);
                     const float dep = s == 0 ? ax0.x : ax1.x;
@@ -344,26 +352,24 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_mlp_round(const __grid_consta
             P.res_rgbd[e] = make_float4(cr, cg, cb, cd);
             P.res_a[e] = ca;
         }
-        // rays that go on: append to the next round's live list (one atomic per warp)
+        // rays that go on: append to the next round's live list (one atomic per warp), finished by flush_append()
         const uint32_t go = __ballot_sync(0xffffffffu, alive);
         if (go) {
             const int leader = __ffs(go) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(Q.cnt_out, (uint32_t)__popc(go));
-            pend_go = go; pend_base = base; pend_alive = alive; pend_e = e;      // finished by flush_append()
+            pend_go = go; pend_base = base; pend_alive = alive; pend_e = e;
             pend_a4 = make_float4(cr, cg, cb, cd); pend_aa = ca;
         }
-        tc_fence_before();
-        __syncthreads();      // every thread has read its output rows: the next block's first MMAs may overwrite the TMEM columns
     }
     flush_append();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) { tc_fence_after(); tmem_dealloc<128>(tmem_base); }
+    if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc<512>(tmem_all); }
     if (P.n_samples || P.prof) {
         for (int o = 16; o > 0; o >>= 1) my_samples += __shfl_xor_sync(0xffffffffu, my_samples, o);
         for (int o = 16; o > 0; o >>= 1) my_rays += __shfl_xor_sync(0xffffffffu, my_rays, o);
-        if ((tid & 31) == 0) {
+        if (lane == 0) {
             if (P.n_samples && my_samples) atomicAdd(P.n_samples, my_samples);
             if (P.prof && my_samples) atomicAdd(P.prof, my_samples);
             if (P.prof && my_rays) atomicAdd(P.prof + 1, my_rays);
