@@ -323,7 +323,7 @@ def run_ours(args):
             f = min(args.chunk, K) / summ["candidates_per_launch"]
             traffic = summ["dram_bytes_per_launch"] * f
             l2_traffic = summ.get("lts_bytes_per_launch", 0) * f or None
-            traffic_note = "ncu dram__bytes_read+write.sum / lts__t_bytes.sum of k_march_ws, scaled to this launch size (profiles/march_ncu_summary.json)"
+            traffic_note = "ncu dram__bytes_read+write.sum / lts__t_bytes.sum over all march kernels of one launch, scaled to this launch size (profiles/march_ncu_summary.json)"
     except Exception:
         pass
     total = m["total"]
@@ -346,7 +346,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(K * 4), "ms_per_step": m["ms_e2e"] / steps,
                 "path": "renderer.iter_render -> ClipVision.encode_images -> ClipVision.score per chunk (what optimise_pose_grid runs), pinned host poses in, pinned host scores out"},
         "gpu_launches": m["launches"],
-        "roofline": {"kernel": "k_march_ws (the ray march of one launch of `chunk` candidates: one persistent warp-specialised kernel)", "bound": "hbm",
+        "roofline": {"kernel": "the ray march of one launch of `chunk` candidates: k_classify, 16 x (k_gather_round, k_mlp_round), k_march_ws (persistent tail), k_finish", "bound": "hbm",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "l2_traffic": l2_traffic,
                      "traffic_note": traffic_note, "algorithmic_bytes_per_launch": alg_bytes / max(1, m["march_launches"]), "peak_source": peak_src,
                      "launches": m["march_launches"], "launches_per_step": launches_per_step,
