@@ -244,3 +244,20 @@ def test_background_depth_rectification_matches_reference_recipe():
     np.putmask(d1, r.rectify_mask(mask, r.resolution) == 0, np.float32(100))
     assert np.array_equal(d1, d4[..., 0])
     assert np.array_equal(r.rectify_depth(depth, r.resolution)[..., 2], cv2.resize(crop, (96, 96), interpolation=cv2.INTER_CUBIC))
+
+
+def test_cpu_arm_banded_pipeline_matches_per_candidate_pipeline():
+    """bench.py's CPU arms: `--impl reference` deals every candidate's pixel rows out over the worker processes (so that a step
+    can be shorter than one candidate on one core), the `cpu_baseline` leg renders one candidate per worker.  Same oracle, same
+    rays, same composite -> identical scores."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    grid = [4, 4, 1, 1, 1, 1]
+    whole = bench.cpu_pipeline("shopping", grid, 16, 96, "ViT-B/32", 12, 2, split=1)
+    a = np.asarray(whole([1, 10]))
+    whole.close()
+    banded = bench.cpu_pipeline("shopping", grid, 16, 96, "ViT-B/32", 12, 2, split=3)
+    b = np.asarray(banded([1, 10]))
+    banded.close()
+    assert a.shape == (2,) and np.isfinite(a).all()
+    assert np.array_equal(a, b)
